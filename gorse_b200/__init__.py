@@ -1,0 +1,244 @@
+"""gorse_b200 -- B200 (sm_100a) implementation of Gorse's collaborative-filtering training and
+brute-force top-k hot path.
+
+The product is the C-ABI shared library (include/gorse_b200.h, gorse_b200/libgorse_b200.so).  This
+package is the thin Python binding over that ABI used by the tests and by bench.py; it holds no
+compute of its own and has no CPU fallback (importing it without the built library fails).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (GorseB200Error, METRIC_EUCLIDEAN, METRIC_NEG_DOT, ORDER_HOGWILD, ORDER_SEQUENTIAL,  # noqa: F401
+                   SCATTER_ATOMIC, SCATTER_STORE, check, lib, ptr)
+
+__all__ = ["Context", "CFModel", "BruteforceIndex", "GorseB200Error", "csr_from_lists", "device_count"]
+
+
+def device_count():
+    n = C.c_int32(0)
+    check(lib.gorse_b200_device_count(C.byref(n)))
+    return n.value
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(_lib.NCCL_ID_BYTES)
+    check(lib.gorse_b200_nccl_unique_id(buf))
+    return buf.raw
+
+
+class PinnedArray:
+    """numpy view of page-locked host memory from gorse_b200_host_alloc (the shim's flat factor mirror)."""
+
+    def __init__(self, shape, dtype=np.float32):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(lib.gorse_b200_host_alloc(self.nbytes, C.byref(p)))
+        self._p = p
+        buf = (C.c_char * self.nbytes).from_address(p.value) if self.nbytes else (C.c_char * 0)()
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            lib.gorse_b200_host_free(self._p)
+            self._p = None
+
+
+def csr_from_lists(rows):
+    """[][]int32 (dataset.CFSplit.GetUserFeedback, dataset/dataset.go:40-60) -> (offsets int64, indices int32)."""
+    off = np.zeros(len(rows) + 1, np.int64)
+    for r, row in enumerate(rows):
+        off[r + 1] = off[r] + len(row)
+    idx = np.zeros(int(off[-1]), np.int32)
+    for r, row in enumerate(rows):
+        idx[off[r]:off[r + 1]] = row
+    return off, idx
+
+
+def transpose_csr(off, idx, n_cols):
+    """user CSR -> item CSR preserving the reference's append order (dataset.go:231-240: users ascending)."""
+    n_rows = len(off) - 1
+    counts = np.bincount(idx, minlength=n_cols).astype(np.int64)
+    toff = np.zeros(n_cols + 1, np.int64)
+    np.cumsum(counts, out=toff[1:])
+    rows = np.repeat(np.arange(n_rows, dtype=np.int32), np.diff(off))
+    order = np.argsort(idx, kind="stable")
+    return toff, rows[order].astype(np.int32)
+
+
+class Context:
+    """One GPU (+ optionally one NCCL rank)."""
+
+    def __init__(self, device=0, rank=0, world=1, nccl_id=None):
+        h = C.c_void_p()
+        if world > 1:
+            check(lib.gorse_b200_ctx_create_dist(device, rank, world, nccl_id, C.byref(h)))
+        else:
+            check(lib.gorse_b200_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.rank, self.world = rank, world
+
+    def close(self):
+        if self.h:
+            lib.gorse_b200_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        check(lib.gorse_b200_ctx_sync(self.h))
+
+    def barrier(self):
+        check(lib.gorse_b200_ctx_barrier(self.h))
+
+    def flush_l2(self):
+        check(lib.gorse_b200_ctx_flush_l2(self.h))
+
+    def timer_begin(self):
+        check(lib.gorse_b200_ctx_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_float(0)
+        check(lib.gorse_b200_ctx_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        n = C.c_int64(0)
+        check(lib.gorse_b200_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class CFModel:
+    """Device-resident factor tables + feedback CSR (cf.BaseMatrixFactorization state)."""
+
+    def __init__(self, ctx, n_users, n_items, n_factors, user_off, user_items, item_off=None, item_users=None):
+        self.ctx = ctx
+        self.n_users, self.n_items, self.d = n_users, n_items, n_factors
+        user_off = np.ascontiguousarray(user_off, np.int64)
+        user_items = np.ascontiguousarray(user_items, np.int32)
+        if item_off is not None:
+            item_off = np.ascontiguousarray(item_off, np.int64)
+            item_users = np.ascontiguousarray(item_users, np.int32)
+        h = C.c_void_p()
+        check(lib.gorse_b200_cf_create(ctx.h, n_users, n_items, n_factors, ptr(user_off), ptr(user_items),
+                                       ptr(item_off), ptr(item_users), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib.gorse_b200_cf_destroy(self.h)
+            self.h = None
+
+    def set_factors(self, P, Q):
+        P = np.ascontiguousarray(P, np.float32)
+        Q = np.ascontiguousarray(Q, np.float32)
+        assert P.shape == (self.n_users, self.d) and Q.shape == (self.n_items, self.d)
+        check(lib.gorse_b200_cf_set_factors(self.h, ptr(P), ptr(Q)))
+
+    def init_normal(self, mean, std, seed):
+        check(lib.gorse_b200_cf_init_normal(self.h, mean, std, seed))
+
+    def get_factors(self, P=None, Q=None):
+        if P is None:
+            P = np.zeros((self.n_users, self.d), np.float32)
+        if Q is None:
+            Q = np.zeros((self.n_items, self.d), np.float32)
+        check(lib.gorse_b200_cf_get_factors(self.h, ptr(P), ptr(Q)))
+        return P, Q
+
+    def predict(self, users, items):
+        users = np.ascontiguousarray(users, np.int32)
+        items = np.ascontiguousarray(items, np.int32)
+        out = np.zeros(users.size, np.float32)
+        check(lib.gorse_b200_cf_predict(self.h, ptr(users), ptr(items), users.size, ptr(out)))
+        return out
+
+    def bpr_apply_triples(self, uij, lr, reg, scatter=SCATTER_STORE, order=ORDER_HOGWILD):
+        uij = np.ascontiguousarray(uij, np.int32).reshape(-1, 3)
+        check(lib.gorse_b200_bpr_apply_triples(self.h, ptr(uij), uij.shape[0], lr, reg, scatter, order))
+
+    def bpr_sample_triples(self, seed, first_step, n):
+        out = np.zeros((n, 3), np.int32)
+        check(lib.gorse_b200_bpr_sample_triples(self.h, seed, first_step, n, ptr(out)))
+        return out
+
+    def bpr_epoch(self, lr, reg, n_steps, seed, scatter=SCATTER_ATOMIC):
+        check(lib.gorse_b200_bpr_epoch(self.h, lr, reg, n_steps, seed, scatter))
+
+    def als_epoch(self, reg, alpha):
+        check(lib.gorse_b200_als_epoch(self.h, reg, alpha))
+
+    def evaluate(self, test_off, test_items, neg_off, neg_items, topk=10):
+        test_off = np.ascontiguousarray(test_off, np.int64)
+        test_items = np.ascontiguousarray(test_items, np.int32)
+        neg_off = np.ascontiguousarray(neg_off, np.int64)
+        neg_items = np.ascontiguousarray(neg_items, np.int32)
+        out = np.zeros(3, np.float32)
+        check(lib.gorse_b200_cf_evaluate(self.h, ptr(test_off), ptr(test_items), ptr(neg_off), ptr(neg_items), topk,
+                                         ptr(out)))
+        return out
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class BruteforceIndex:
+    """ann.Index backed by the GPU (common/ann/ann.go:21-25, bruteforce.go:24-83)."""
+
+    def __init__(self, ctx, dim, metric=METRIC_NEG_DOT):
+        self.ctx, self.dim, self.metric = ctx, dim, metric
+        h = C.c_void_p()
+        check(lib.gorse_b200_index_create(ctx.h, dim, metric, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib.gorse_b200_index_destroy(self.h)
+            self.h = None
+
+    def add(self, vectors):
+        """Bruteforce.Add for a batch; returns len after append (bruteforce.go:33-37)."""
+        v = np.ascontiguousarray(vectors, np.float32).reshape(-1, self.dim)
+        n = C.c_int64(0)
+        check(lib.gorse_b200_index_add(self.h, ptr(v), v.shape[0], C.byref(n)))
+        return n.value
+
+    def __len__(self):
+        n = C.c_int64(0)
+        check(lib.gorse_b200_index_len(self.h, C.byref(n)))
+        return n.value
+
+    def _out(self, nq, k):
+        return (np.full((nq, max(k, 1)), -1, np.int32), np.zeros((nq, max(k, 1)), np.float32), np.zeros(nq, np.int32))
+
+    def search_vectors(self, queries, k, prune0=False):
+        q = np.ascontiguousarray(queries, np.float32).reshape(-1, self.dim)
+        idx, dist, cnt = self._out(q.shape[0], k)
+        check(lib.gorse_b200_index_search_vectors(self.h, ptr(q), q.shape[0], k, int(prune0), ptr(idx), ptr(dist), ptr(cnt)))
+        return idx, dist, cnt
+
+    def search_indices(self, q_idx, k, prune0=False):
+        q = np.ascontiguousarray(q_idx, np.int64)
+        idx, dist, cnt = self._out(q.size, k)
+        check(lib.gorse_b200_index_search_indices(self.h, ptr(q), q.size, k, int(prune0), ptr(idx), ptr(dist), ptr(cnt)))
+        return idx, dist, cnt
+
+    def search_range(self, q0, q1, k, prune0=False):
+        idx, dist, cnt = self._out(max(q1 - q0, 0), k)
+        check(lib.gorse_b200_index_search_range(self.h, q0, q1, k, int(prune0), ptr(idx), ptr(dist), ptr(cnt)))
+        return idx, dist, cnt
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()

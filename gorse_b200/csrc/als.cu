@@ -1,0 +1,313 @@
+// als.cu -- eALS ("CCD") epoch: model/cf/model.go:641-738.
+//   S^q = sum_{i: |R_i|>0} q_i q_i^T          (:645-658)   gram_kernel + gram_reduce_kernel
+//   user rows, coordinate descent over f      (:659-687)   als_rows_kernel
+//   S^p = sum_{u: |R_u|>0} p_u p_u^T          (:693-706)
+//   item rows                                 (:707-735)
+// Roofline class: HBM bandwidth (one gather of the opposite table's rows per feedback + own row + one
+// Gram pass): B_epoch = 2|R|(4d+4) + 3(U+I)4d bytes.
+//
+// Row kernel: one warp per row.  The gathered rows Y[R_x] are staged once in shared memory
+// ([n][d+1], the +1 makes the per-f column walk conflict-free), the running predictions live in
+// registers, and the strictly sequential f loop costs two warp reductions per factor.  Sums over the
+// row's feedback are taken lane-parallel, so a/c/b differ from the reference's serial order by
+// reassociation only (parity budget 1e-4 relative, observed ~1e-6).
+#include <algorithm>
+
+#include "cf.cuh"
+
+namespace gb {
+
+#define GB_ALS_PRED_REGS 4      // rows up to 128 entries keep pred in registers
+#define GB_ALS_WARPS 4          // warps per CTA in the row kernel
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// Partial Gram of rows [r0, r1) handled by this CTA; TxT register tile per thread, 16x16 threads.
+template <int T>
+__global__ void __launch_bounds__(256) gram_kernel(const float *X, int32_t rows, int d, const int64_t *off, float *partial)
+{
+    extern __shared__ float xs[];  // [16][dp]
+    const int dp = 16 * T;         // padded width
+    const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+    float acc[T][T];
+#pragma unroll
+    for (int a = 0; a < T; a++)
+#pragma unroll
+        for (int b = 0; b < T; b++) acc[a][b] = 0.f;
+    int64_t per = ((int64_t)rows + gridDim.x - 1) / gridDim.x;
+    int64_t r0 = (int64_t)blockIdx.x * per, r1 = min((int64_t)rows, r0 + per);
+    for (int64_t base = r0; base < r1; base += 16) {
+        // stage 16 rows (zero-filled when masked or out of range)
+        for (int e = threadIdx.x; e < 16 * dp; e += 256) {
+            int rr = e / dp, k = e - rr * dp;
+            int64_t r = base + rr;
+            float v = 0.f;
+            if (r < r1 && k < d && off[r + 1] > off[r]) v = X[r * d + k];
+            xs[e] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < 16; rr++) {
+            float a[T], b[T];
+#pragma unroll
+            for (int k = 0; k < T; k++) { a[k] = xs[rr * dp + ti * T + k]; b[k] = xs[rr * dp + tj * T + k]; }
+#pragma unroll
+            for (int x = 0; x < T; x++)
+#pragma unroll
+                for (int y = 0; y < T; y++) acc[x][y] = __fmaf_rn(a[x], b[y], acc[x][y]);
+        }
+        __syncthreads();
+    }
+    float *out = partial + (int64_t)blockIdx.x * d * d;
+#pragma unroll
+    for (int x = 0; x < T; x++)
+#pragma unroll
+        for (int y = 0; y < T; y++) {
+            int i = ti * T + x, j = tj * T + y;
+            if (i < d && j < d) out[i * d + j] = acc[x][y];
+        }
+}
+
+// generic d > 128: one thread per output element, rows streamed from global
+__global__ void gram_generic_kernel(const float *X, int32_t rows, int d, const int64_t *off, float *partial)
+{
+    int64_t per = ((int64_t)rows + gridDim.x - 1) / gridDim.x;
+    int64_t r0 = (int64_t)blockIdx.x * per, r1 = min((int64_t)rows, r0 + per);
+    float *out = partial + (int64_t)blockIdx.x * d * d;
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+        int i = e / d, j = e - i * d;
+        float acc = 0.f;
+        for (int64_t r = r0; r < r1; r++)
+            if (off[r + 1] > off[r]) acc = __fmaf_rn(X[r * d + i], X[r * d + j], acc);
+        out[e] = acc;
+    }
+}
+
+// fixed-order reduction of the per-CTA partials: deterministic run to run
+__global__ void gram_reduce_kernel(const float *partial, int n_parts, int dd, float *S)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= dd) return;
+    float s = 0.f;
+    for (int p = 0; p < n_parts; p++) s += partial[(int64_t)p * dd + e];
+    S[e] = s;
+}
+
+// One warp per row.  X: table being updated (row index r - x_lo), Y: the opposite table (index y - y_lo).
+// smem per warp: xrow[d] + (staged ? ys[cap_n][d+1] : 0)
+__global__ void __launch_bounds__(32 * GB_ALS_WARPS)
+als_rows_kernel(float *X, const float *Y, int d, int32_t x_lo, int32_t y_lo, const int64_t *off, const int32_t *idx,
+                const float *S, float reg, float w, const int32_t *row_ids, int32_t n_rows, int stage_floats_per_warp,
+                float *pred_scratch)
+{
+    extern __shared__ float smem[];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int per_warp = d + stage_floats_per_warp;
+    float *xrow = smem + (size_t)wid * per_warp;
+    float *ys = xrow + d;
+    const int dp = d + 1;
+    const float omw = 1.0f - w;
+    int32_t slot = blockIdx.x * GB_ALS_WARPS + wid;
+    const int32_t n_slots = gridDim.x * GB_ALS_WARPS;
+    for (; slot < n_rows; slot += n_slots) {
+        const int32_t r = row_ids[slot];
+        const int64_t o = off[r];
+        const int n = (int)(off[r + 1] - o);
+        float *xg = X + (int64_t)(r - x_lo) * d;
+        for (int k = lane; k < d; k += 32) xrow[k] = xg[k];
+        const bool staged = (int64_t)n * dp <= stage_floats_per_warp;
+        const bool pred_in_regs = n <= 32 * GB_ALS_PRED_REGS;
+        float *pg = pred_scratch + o;
+        __syncwarp();
+        if (staged) {
+            // coalesced row copies: lane walks the row, one row at a time
+            for (int t = 0; t < n; t++) {
+                const float *yr = Y + (int64_t)(idx[o + t] - y_lo) * d;
+                for (int k = lane; k < d; k += 32) ys[t * dp + k] = yr[k];
+            }
+            __syncwarp();
+        }
+        // pred[t] = internalPredict = floats.Dot(x, y_t)   (:661-663)
+        float pr[GB_ALS_PRED_REGS];
+#pragma unroll
+        for (int q = 0; q < GB_ALS_PRED_REGS; q++) pr[q] = 0.f;
+        for (int t0 = 0; t0 < n; t0 += 32) {
+            int t = t0 + lane;
+            float v = 0.f;
+            if (t < n) {
+                if (staged) {
+                    // same order as dot_any on the staged copy
+                    const float *yr = ys + t * dp;
+                    v = dot_any(xrow, yr, d);
+                } else {
+                    v = dot_any(xrow, Y + (int64_t)(idx[o + t] - y_lo) * d, d);
+                }
+            }
+            if (pred_in_regs) {
+#pragma unroll
+                for (int q = 0; q < GB_ALS_PRED_REGS; q++) if (t0 == 32 * q) pr[q] = v;
+            } else if (t < n) pg[t] = v;
+        }
+        for (int f = 0; f < d; f++) {
+            const float xf = xrow[f];
+            float a = 0.f, c = 0.f, b = 0.f;
+            // :666-674
+            for (int t0 = 0, q = 0; t0 < n; t0 += 32, q++) {
+                int t = t0 + lane;
+                if (t < n) {
+                    float y = staged ? ys[t * dp + f] : __ldg(Y + (int64_t)(idx[o + t] - y_lo) * d + f);
+                    float p;
+                    if (pred_in_regs) {
+                        p = pr[0];
+#pragma unroll
+                        for (int qq = 1; qq < GB_ALS_PRED_REGS; qq++) if (q == qq) p = pr[qq];
+                    } else p = pg[t];
+                    float res = p - xf * y;
+                    a = a + (1.0f - omw * res) * y;
+                    c = c + (omw * y) * y;
+                }
+            }
+            // :675-679   S is bitwise symmetric, so read row f (contiguous) instead of column f
+            for (int k = lane; k < d; k += 32)
+                if (k != f) b = b + (w * xrow[k]) * __ldg(S + f * d + k);
+            a = warp_sum(a);
+            c = warp_sum(c);
+            b = warp_sum(b);
+            const float xn = (a - b) / ((c + w * __ldg(S + f * d + f)) + reg);  // :680
+            // :682-684
+            for (int t0 = 0, q = 0; t0 < n; t0 += 32, q++) {
+                int t = t0 + lane;
+                if (t < n) {
+                    float y = staged ? ys[t * dp + f] : __ldg(Y + (int64_t)(idx[o + t] - y_lo) * d + f);
+                    if (pred_in_regs) {
+#pragma unroll
+                        for (int qq = 0; qq < GB_ALS_PRED_REGS; qq++)
+                            if (q == qq) { float res = pr[qq] - xf * y; pr[qq] = res + xn * y; }
+                    } else {
+                        float res = pg[t] - xf * y;
+                        pg[t] = res + xn * y;
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) xrow[f] = xn;
+            __syncwarp();
+        }
+        for (int k = lane; k < d; k += 32) xg[k] = xrow[k];
+        __syncwarp();
+    }
+}
+
+static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const int64_t *off)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    const int d = cf->d, dd = d * d;
+    int parts = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, (int64_t)c->sm_count * 2));
+    size_t need = (size_t)parts * dd;
+    if (cf->scratch.n < need) GB_TRY(cf->scratch.alloc(need));
+    if (d <= 128) {
+        int T = d <= 16 ? 1 : d <= 32 ? 2 : d <= 64 ? 4 : 8;
+        size_t sm = sizeof(float) * 16 * 16 * T;
+        switch (T) {
+            case 1: gram_kernel<1><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            case 2: gram_kernel<2><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            case 4: gram_kernel<4><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            default: gram_kernel<8><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+        }
+    } else {
+        gram_generic_kernel<<<parts, 256, 0, c->stream>>>(X, rows, d, off, cf->scratch.p);
+    }
+    GB_LAUNCHED(c);
+    gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, c->stream>>>(cf->scratch.p, parts, dd, cf->gram.p);
+    GB_LAUNCHED(c);
+    return GORSE_B200_OK;
+}
+
+// rows bucketed by length so that each launch has a shared-memory budget that fits its rows:
+//   class 0: n*(d+1) <= 3072 floats  (12 KB/warp, 4 CTAs/SM)
+//   class 1: n*(d+1) <= 12288 floats (48 KB/warp, 1 CTA/SM)
+//   class 2: longer rows, gathered from L2 (no staging)
+static const int kStageFloats[3] = {3072, 12288, 0};
+
+static int32_t prepare_als(gorse_b200_cf *cf)
+{
+    if (cf->als_ready) return GORSE_B200_OK;
+    const int dp = cf->d + 1;
+    for (int side = 0; side < 2; side++) {
+        const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
+        int32_t rows = side == 0 ? cf->n_users : cf->n_items;
+        std::vector<int32_t> cls[3];
+        for (int32_t r = 0; r < rows; r++) {
+            int64_t n = off[(size_t)r + 1] - off[r];
+            int k = n * dp <= kStageFloats[0] ? 0 : n * dp <= kStageFloats[1] ? 1 : 2;
+            cls[k].push_back(r);
+        }
+        for (int k = 0; k < 3; k++) {
+            // longest rows first inside a class: better tail behaviour
+            std::stable_sort(cls[k].begin(), cls[k].end(), [&](int32_t a, int32_t b) {
+                return off[(size_t)a + 1] - off[a] > off[(size_t)b + 1] - off[b];
+            });
+            cf->als_rows_n[side][k] = (int32_t)cls[k].size();
+            GB_TRY(cf->als_rows[side][k].alloc(cls[k].size()));
+            if (!cls[k].empty())
+                GB_CUDA(cudaMemcpy(cf->als_rows[side][k].p, cls[k].data(), sizeof(int32_t) * cls[k].size(), cudaMemcpyHostToDevice));
+        }
+    }
+    GB_TRY(cf->gram.alloc((size_t)cf->d * cf->d));
+    GB_CUDA(cudaFuncSetAttribute(als_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    cf->als_ready = true;
+    return GORSE_B200_OK;
+}
+
+static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, const int64_t *off, const int32_t *idx,
+                        float reg, float w, float *pred_scratch)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    for (int k = 0; k < 3; k++) {
+        int32_t n_rows = cf->als_rows_n[side][k];
+        if (n_rows == 0) continue;
+        size_t sm = sizeof(float) * GB_ALS_WARPS * (size_t)(cf->d + kStageFloats[k]);
+        int ctas_per_sm = k == 0 ? 4 : 1;
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + GB_ALS_WARPS - 1) / GB_ALS_WARPS, (int64_t)c->sm_count * ctas_per_sm * (k == 2 ? 8 : 1)));
+        als_rows_kernel<<<grid, 32 * GB_ALS_WARPS, sm, c->stream>>>(X, Y, cf->d, 0, 0, off, idx, cf->gram.p, reg, w,
+                                                                  cf->als_rows[side][k].p, n_rows, kStageFloats[k], pred_scratch);
+        GB_LAUNCHED(c);
+    }
+    return GORSE_B200_OK;
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alpha)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    if (!cf->has_item_csr) { set_error("als_epoch needs the item CSR (item_off/item_users) at cf_create"); return GORSE_B200_ERR_STATE; }
+    if (cf->ctx->world != 1) { set_error("als_epoch is single-GPU in this round (world must be 1)"); return GORSE_B200_ERR_UNSUPPORTED; }
+    ScopedDevice sd(cf->ctx->device);
+    GB_TRY(prepare_als(cf));
+    DevBuf<float> pred;
+    GB_TRY(pred.alloc((size_t)std::max<int64_t>(1, cf->n_feedback)));
+    int32_t st;
+    auto done = [&](int32_t s) {
+        cudaStreamSynchronize(cf->ctx->stream);
+        pred.free();
+        return s;
+    };
+    if ((st = run_gram(cf, cf->Q.p, cf->n_items, cf->item_off.p))) return done(st);
+    if ((st = run_rows(cf, 0, cf->P.p, cf->Q.p, cf->user_off.p, cf->user_items.p, reg, alpha, pred.p))) return done(st);
+    if ((st = run_gram(cf, cf->P.p, cf->n_users, cf->user_off.p))) return done(st);
+    if ((st = run_rows(cf, 1, cf->Q.p, cf->P.p, cf->item_off.p, cf->item_users.p, reg, alpha, pred.p))) return done(st);
+    cudaError_t e = cudaStreamSynchronize(cf->ctx->stream);
+    if (e != cudaSuccess) { set_error("als_epoch: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    return done(GORSE_B200_OK);
+}

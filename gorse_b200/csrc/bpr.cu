@@ -1,0 +1,453 @@
+// bpr.cu -- BPR pairwise SGD: the fused sample-gather-dot-sigmoid-scatter kernel.
+// Replaces the body of BPR.Fit's epoch loop, model/cf/model.go:448-490 (arithmetic: SURVEY Appendix A).
+//
+// Roofline class: HBM/L2 bandwidth.  Algorithmic bytes per triple = 6*d*4 + 12 (3 rows read, 3 rows
+// written, 3 ids).  One quad (4 lanes) owns one triple; see cf.cuh for the row->lane mapping that keeps
+// the reference's AVX-512 summation order with 128-bit coalesced loads.
+#include <algorithm>
+
+#include "cf.cuh"
+
+namespace gb {
+
+struct BprView {
+    float *P, *Q;
+    const int64_t *user_off;
+    const int32_t *user_items;
+    const int32_t *active;
+    int32_t n_active, n_items, d, u_lo;
+};
+
+// factor rows are read and written by every SM concurrently: keep them out of the (non-coherent) L1
+__device__ __forceinline__ float4 ld_row(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st_row(float *p, float4 v) { __stcg(reinterpret_cast<float4 *>(p), v); }
+__device__ __forceinline__ void red_row(float *p, float4 v)
+{
+    asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+#define GB_F4_OP(dst, expr)                            \
+    do {                                               \
+        { const int k_ = 0; (dst).x = (expr); }        \
+        { const int k_ = 1; (dst).y = (expr); }        \
+        { const int k_ = 2; (dst).z = (expr); }        \
+        { const int k_ = 3; (dst).w = (expr); }        \
+    } while (0)
+__device__ __forceinline__ float f4get(const float4 &v, int k) { return k == 0 ? v.x : k == 1 ? v.y : k == 2 ? v.z : v.w; }
+
+// gradient of -log sigmoid: model.go:471  grad = exp(-diff) / (1 + exp(-diff))   (NaN when exp overflows)
+__device__ __forceinline__ float bpr_grad(float diff)
+{
+    float e = exp_math32(-diff);
+    return __fdiv_rn(e, __fadd_rn(1.0f, e));
+}
+
+// one SGD step by a quad, rows held in registers.  C = d / 16 chunks.
+template <int C, bool ATOMIC>
+__device__ __forceinline__ void bpr_step_quad(float *Pu, float *Qi, float *Qj, int lane4, unsigned mask, float lr, float reg)
+{
+    float4 p[C], qi[C], qj[C];
+    Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
+#pragma unroll
+    for (int c = 0; c < C; c++) p[c] = ld_row(Pu + 16 * c);
+#pragma unroll
+    for (int c = 0; c < C; c++) qi[c] = ld_row(Qi + 16 * c);
+#pragma unroll
+    for (int c = 0; c < C; c++) qj[c] = ld_row(Qj + 16 * c);
+    float4 ai = make_float4(0.f, 0.f, 0.f, 0.f), aj = ai;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        dot_chunk(ai, p[c], qi[c], c == 0);
+        dot_chunk(aj, p[c], qj[c], c == 0);
+    }
+    float diff = __fsub_rn(quad_tree(ai, mask), quad_tree(aj, mask));  // :469
+    float g = bpr_grad(diff), ng = -g, nreg = -reg;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        float4 t, o;
+        // :477-479  q_i += lr * (g*p - reg*q_i)
+        GB_F4_OP(t, __fmaf_rn(f4get(qi[c], k_), nreg, __fmul_rn(g, f4get(p[c], k_))));
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qi + 16 * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qi[c], k_))); st_row(Qi + 16 * c, o); }
+        // :481-483  q_j += lr * (-g*p - reg*q_j)
+        GB_F4_OP(t, __fmaf_rn(f4get(qj[c], k_), nreg, __fmul_rn(ng, f4get(p[c], k_))));
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qj + 16 * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qj[c], k_))); st_row(Qj + 16 * c, o); }
+        // :485-488  p_u += lr * (g*(q_i - q_j) - reg*p_u)
+        GB_F4_OP(t, __fmaf_rn(f4get(p[c], k_), nreg, __fmul_rn(__fsub_rn(f4get(qi[c], k_), f4get(qj[c], k_)), g)));
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Pu + 16 * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(p[c], k_))); st_row(Pu + 16 * c, o); }
+    }
+}
+
+// same step for any d % 16 == 0 without register-resident rows (two passes over L2-hot rows)
+template <bool ATOMIC>
+__device__ __forceinline__ void bpr_step_quad_dyn(float *Pu, float *Qi, float *Qj, int chunks, int lane4, unsigned mask,
+                                                  float lr, float reg)
+{
+    Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
+    float4 ai = make_float4(0.f, 0.f, 0.f, 0.f), aj = ai;
+    for (int c = 0; c < chunks; c++) {
+        float4 p = ld_row(Pu + 16 * c);
+        dot_chunk(ai, p, ld_row(Qi + 16 * c), c == 0);
+        dot_chunk(aj, p, ld_row(Qj + 16 * c), c == 0);
+    }
+    float diff = __fsub_rn(quad_tree(ai, mask), quad_tree(aj, mask));
+    float g = bpr_grad(diff), ng = -g, nreg = -reg;
+    for (int c = 0; c < chunks; c++) {
+        float4 p = ld_row(Pu + 16 * c), qi = ld_row(Qi + 16 * c), qj = ld_row(Qj + 16 * c), t, o;
+        GB_F4_OP(t, __fmaf_rn(f4get(qi, k_), nreg, __fmul_rn(g, f4get(p, k_))));
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qi + 16 * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qi, k_))); st_row(Qi + 16 * c, o); }
+        GB_F4_OP(t, __fmaf_rn(f4get(qj, k_), nreg, __fmul_rn(ng, f4get(p, k_))));
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qj + 16 * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qj, k_))); st_row(Qj + 16 * c, o); }
+        GB_F4_OP(t, __fmaf_rn(f4get(p, k_), nreg, __fmul_rn(__fsub_rn(f4get(qi, k_), f4get(qj, k_)), g)));
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Pu + 16 * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(p, k_))); st_row(Pu + 16 * c, o); }
+    }
+}
+
+template <int C, bool ATOMIC>
+__device__ __forceinline__ void bpr_step_dispatch(float *Pu, float *Qi, float *Qj, int d, int lane4, unsigned mask,
+                                                  float lr, float reg)
+{
+    if (C > 0) bpr_step_quad<(C > 0 ? C : 1), ATOMIC>(Pu, Qi, Qj, lane4, mask, lr, reg);
+    else bpr_step_quad_dyn<ATOMIC>(Pu, Qi, Qj, d / 16, lane4, mask, lr, reg);
+}
+
+// any d (d % 16 != 0: 8-lane block and fused scalar tails as in the reference), one thread per triple
+template <bool ATOMIC>
+__device__ inline void bpr_step_any(float *Pu, float *Qi, float *Qj, int d, float lr, float reg)
+{
+    float diff = __fsub_rn(dot_any(Pu, Qi, d), dot_any(Pu, Qj, d));
+    float g = bpr_grad(diff), ng = -g, nreg = -reg;
+    for (int k = 0; k < d; k++) {
+        float p = __ldcg(Pu + k), qi = __ldcg(Qi + k), qj = __ldcg(Qj + k);
+        float t = axpy_elem(qi, nreg, __fmul_rn(p, g), k, d);
+        if (ATOMIC) atomicAdd(Qi + k, __fmul_rn(t, lr)); else Qi[k] = axpy_elem(t, lr, qi, k, d);
+        t = axpy_elem(qj, nreg, __fmul_rn(p, ng), k, d);
+        if (ATOMIC) atomicAdd(Qj + k, __fmul_rn(t, lr)); else Qj[k] = axpy_elem(t, lr, qj, k, d);
+        t = axpy_elem(p, nreg, __fmul_rn(__fsub_rn(qi, qj), g), k, d);
+        if (ATOMIC) atomicAdd(Pu + k, __fmul_rn(t, lr)); else Pu[k] = axpy_elem(t, lr, p, k, d);
+    }
+}
+
+// sampling, model.go:449-468 (distribution) on the counter RNG
+__device__ __forceinline__ void sample_triple(const BprView &v, uint64_t base, int64_t step, int32_t &u, int32_t &i,
+                                              int32_t &j)
+{
+    SStream s;
+    s.x = mix64(base + (uint64_t)step);
+    u = __ldg(v.active + s.bounded((uint32_t)v.n_active));
+    int64_t o = __ldg(v.user_off + u), len = __ldg(v.user_off + u + 1) - o;
+    i = __ldg(v.user_items + o + s.bounded((uint32_t)len));
+    j = -1;
+    if (len < v.n_items) {
+        for (;;) {
+            int32_t c = (int32_t)s.bounded((uint32_t)v.n_items);
+            if (!row_contains(v.user_items + o, len, c)) { j = c; break; }
+        }
+    }
+}
+
+// ---- kernels -----------------------------------------------------------------------------------
+template <int C, bool ATOMIC>
+__global__ void __launch_bounds__(256) bpr_epoch_kernel(BprView v, int64_t step0, int64_t n_steps, uint64_t base, float lr, float reg)
+{
+    const int lane4 = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int64_t nq = ((int64_t)gridDim.x * blockDim.x) >> 2;
+    for (; q < n_steps; q += nq) {
+        int32_t u, i, j;
+        sample_triple(v, base, step0 + q, u, i, j);
+        if (j < 0) continue;
+        bpr_step_dispatch<C, ATOMIC>(v.P + (int64_t)(u - v.u_lo) * v.d, v.Q + (int64_t)i * v.d, v.Q + (int64_t)j * v.d,
+                                     v.d, lane4, mask, lr, reg);
+    }
+}
+
+template <int C, bool ATOMIC>
+__global__ void __launch_bounds__(256) bpr_apply_kernel(BprView v, const int32_t *uij, int64_t n, float lr, float reg)
+{
+    const int lane4 = threadIdx.x & 3;
+    const unsigned mask = quad_mask();
+    int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const int64_t nq = ((int64_t)gridDim.x * blockDim.x) >> 2;
+    for (; q < n; q += nq) {
+        int32_t u = __ldg(uij + 3 * q), i = __ldg(uij + 3 * q + 1), j = __ldg(uij + 3 * q + 2);
+        if (j < 0) continue;
+        bpr_step_dispatch<C, ATOMIC>(v.P + (int64_t)(u - v.u_lo) * v.d, v.Q + (int64_t)i * v.d, v.Q + (int64_t)j * v.d,
+                                     v.d, lane4, mask, lr, reg);
+    }
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) bpr_epoch_any_kernel(BprView v, int64_t step0, int64_t n_steps, uint64_t base, float lr, float reg)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nq = (int64_t)gridDim.x * blockDim.x;
+    for (; q < n_steps; q += nq) {
+        int32_t u, i, j;
+        sample_triple(v, base, step0 + q, u, i, j);
+        if (j < 0) continue;
+        bpr_step_any<ATOMIC>(v.P + (int64_t)(u - v.u_lo) * v.d, v.Q + (int64_t)i * v.d, v.Q + (int64_t)j * v.d, v.d, lr, reg);
+    }
+}
+
+template <bool ATOMIC>
+__global__ void __launch_bounds__(128) bpr_apply_any_kernel(BprView v, const int32_t *uij, int64_t n, float lr, float reg)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nq = (int64_t)gridDim.x * blockDim.x;
+    for (; q < n; q += nq) {
+        int32_t u = uij[3 * q], i = uij[3 * q + 1], j = uij[3 * q + 2];
+        if (j < 0) continue;
+        bpr_step_any<ATOMIC>(v.P + (int64_t)(u - v.u_lo) * v.d, v.Q + (int64_t)i * v.d, v.Q + (int64_t)j * v.d, v.d, lr, reg);
+    }
+}
+
+__global__ void bpr_sample_kernel(BprView v, uint64_t base, int64_t first, int64_t n, int32_t *out)
+{
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nq = (int64_t)gridDim.x * blockDim.x;
+    for (; q < n; q += nq) {
+        int32_t u, i, j;
+        sample_triple(v, base, first + q, u, i, j);
+        out[3 * q] = u; out[3 * q + 1] = i; out[3 * q + 2] = j;
+    }
+}
+
+// distributed item-factor exchange: Q <- Q - Q0 (local delta); all-reduce; Q <- Q0 + sum; Q0 <- Q
+__global__ void q_delta_kernel(float4 *q, const float4 *q0, int64_t n4)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += st) {
+        float4 a = q[i], b = q0[i];
+        q[i] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+    }
+}
+__global__ void q_apply_kernel(float4 *q, float4 *q0, int64_t n4)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n4; i += st) {
+        float4 a = q[i], b = q0[i];
+        float4 r = make_float4(b.x + a.x, b.y + a.y, b.z + a.z, b.w + a.w);
+        q[i] = r;
+        q0[i] = r;
+    }
+}
+__global__ void q_delta_scalar_kernel(float *q, const float *q0, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) q[i] = q[i] - q0[i];
+}
+__global__ void q_apply_scalar_kernel(float *q, float *q0, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) { float r = q0[i] + q[i]; q[i] = r; q0[i] = r; }
+}
+
+static BprView make_view(gorse_b200_cf *cf)
+{
+    BprView v;
+    v.P = cf->P.p; v.Q = cf->Q.p;
+    v.user_off = cf->user_off.p; v.user_items = cf->user_items.p; v.active = cf->active.p;
+    v.n_active = cf->n_active; v.n_items = cf->n_items; v.d = cf->d; v.u_lo = cf->u_lo;
+    return v;
+}
+
+// grid: persistent, a multiple of the SM count (B200: 148 SMs); 256 threads = 64 quads per CTA
+static int quad_grid(const gorse_b200_ctx *c, int64_t n_quads, int ctas_per_sm)
+{
+    int64_t want = (n_quads + 63) / 64;
+    int64_t cap = (int64_t)c->sm_count * ctas_per_sm;
+    return (int)std::max<int64_t>(1, std::min(want, cap));
+}
+
+template <bool ATOMIC>
+static void launch_epoch(gorse_b200_cf *cf, const BprView &v, int64_t step0, int64_t n, uint64_t base, float lr, float reg)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    cudaStream_t s = c->stream;
+    if (cf->d % 16 == 0) {
+        int C = cf->d / 16;
+        int g = quad_grid(c, n, C <= 4 ? 8 : 4);
+        switch (C) {
+            case 1: bpr_epoch_kernel<1, ATOMIC><<<g, 256, 0, s>>>(v, step0, n, base, lr, reg); break;
+            case 2: bpr_epoch_kernel<2, ATOMIC><<<g, 256, 0, s>>>(v, step0, n, base, lr, reg); break;
+            case 4: bpr_epoch_kernel<4, ATOMIC><<<g, 256, 0, s>>>(v, step0, n, base, lr, reg); break;
+            case 8: bpr_epoch_kernel<8, ATOMIC><<<g, 256, 0, s>>>(v, step0, n, base, lr, reg); break;
+            default: bpr_epoch_kernel<0, ATOMIC><<<g, 256, 0, s>>>(v, step0, n, base, lr, reg); break;
+        }
+    } else {
+        int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)c->sm_count * 8));
+        bpr_epoch_any_kernel<ATOMIC><<<g, 128, 0, s>>>(v, step0, n, base, lr, reg);
+    }
+}
+
+template <bool ATOMIC>
+static void launch_apply(gorse_b200_cf *cf, const BprView &v, const int32_t *d_uij, int64_t n, float lr, float reg)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    cudaStream_t s = c->stream;
+    if (cf->d % 16 == 0) {
+        int C = cf->d / 16;
+        int g = quad_grid(c, n, C <= 4 ? 8 : 4);
+        switch (C) {
+            case 1: bpr_apply_kernel<1, ATOMIC><<<g, 256, 0, s>>>(v, d_uij, n, lr, reg); break;
+            case 2: bpr_apply_kernel<2, ATOMIC><<<g, 256, 0, s>>>(v, d_uij, n, lr, reg); break;
+            case 4: bpr_apply_kernel<4, ATOMIC><<<g, 256, 0, s>>>(v, d_uij, n, lr, reg); break;
+            case 8: bpr_apply_kernel<8, ATOMIC><<<g, 256, 0, s>>>(v, d_uij, n, lr, reg); break;
+            default: bpr_apply_kernel<0, ATOMIC><<<g, 256, 0, s>>>(v, d_uij, n, lr, reg); break;
+        }
+    } else {
+        int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)c->sm_count * 8));
+        bpr_apply_any_kernel<ATOMIC><<<g, 128, 0, s>>>(v, d_uij, n, lr, reg);
+    }
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int32_t gorse_b200_bpr_apply_triples(gorse_b200_cf *cf, const int32_t *uij, int64_t n, float lr, float reg,
+                                     int32_t scatter, int32_t order)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    GB_CHECK_ARG(n >= 0, "negative n");
+    GB_CHECK_ARG(scatter == GORSE_B200_SCATTER_STORE || scatter == GORSE_B200_SCATTER_ATOMIC, "bad scatter mode %d", scatter);
+    GB_CHECK_ARG(order == GORSE_B200_ORDER_HOGWILD || order == GORSE_B200_ORDER_SEQUENTIAL, "bad order %d", order);
+    if (n == 0) return GORSE_B200_OK;
+    GB_CHECK_ARG(uij != nullptr, "uij is NULL");
+    for (int64_t t = 0; t < n; t++) {
+        int32_t u = uij[3 * t], i = uij[3 * t + 1], j = uij[3 * t + 2];
+        if (j < 0) continue;
+        GB_CHECK_ARG(u >= cf->u_lo && u < cf->u_hi, "triple %lld: user %d outside shard [%d, %d)", (long long)t, u, cf->u_lo, cf->u_hi);
+        GB_CHECK_ARG(i >= 0 && i < cf->n_items && j < cf->n_items, "triple %lld: item out of range", (long long)t);
+    }
+    ScopedDevice sd(cf->ctx->device);
+    gorse_b200_ctx *c = cf->ctx;
+    BprView v = make_view(cf);
+    DevBuf<int32_t> d_uij;
+    GB_TRY(d_uij.alloc((size_t)3 * n));
+    auto done = [&](int32_t s) {
+        cudaStreamSynchronize(c->stream);
+        d_uij.free();
+        return s;
+    };
+    auto check = [&]() -> int32_t {
+        c->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("bpr_apply launch: %s", cudaGetErrorString(e));
+            return GORSE_B200_ERR_CUDA;
+        }
+        return GORSE_B200_OK;
+    };
+    if (order == GORSE_B200_ORDER_HOGWILD) {
+        cudaError_t e = cudaMemcpyAsync(d_uij.p, uij, sizeof(int32_t) * 3 * n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { set_error("upload: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+        if (scatter == GORSE_B200_SCATTER_ATOMIC) launch_apply<true>(cf, v, d_uij.p, n, lr, reg);
+        else launch_apply<false>(cf, v, d_uij.p, n, lr, reg);
+        int32_t st = check();
+        if (st) return done(st);
+    } else {
+        // conflict-free waves: wave(t) = 1 + max(last wave that touched u, i or j).  Launching the waves in
+        // order is exactly the reference with Jobs = 1 on this triple stream.
+        std::vector<int32_t> last_u((size_t)(cf->u_hi - cf->u_lo), 0), last_i((size_t)cf->n_items, 0), wave((size_t)n, 0);
+        int32_t n_waves = 0;
+        for (int64_t t = 0; t < n; t++) {
+            int32_t u = uij[3 * t] - cf->u_lo, i = uij[3 * t + 1], j = uij[3 * t + 2];
+            if (j < 0) { wave[t] = 0; continue; }
+            int32_t w = 1 + std::max(last_u[u], std::max(last_i[i], last_i[j]));
+            wave[t] = w;
+            last_u[u] = last_i[i] = last_i[j] = w;
+            n_waves = std::max(n_waves, w);
+        }
+        std::vector<int64_t> start((size_t)n_waves + 2, 0);
+        for (int64_t t = 0; t < n; t++) start[(size_t)wave[t] + 1]++;
+        for (int32_t w = 0; w <= n_waves; w++) start[(size_t)w + 1] += start[w];
+        std::vector<int32_t> sorted((size_t)3 * n);
+        std::vector<int64_t> pos(start.begin(), start.end() - 1);
+        for (int64_t t = 0; t < n; t++) {
+            int64_t p = pos[wave[t]]++;
+            sorted[3 * p] = uij[3 * t]; sorted[3 * p + 1] = uij[3 * t + 1]; sorted[3 * p + 2] = uij[3 * t + 2];
+        }
+        cudaError_t e = cudaMemcpyAsync(d_uij.p, sorted.data(), sizeof(int32_t) * 3 * n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { set_error("upload: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+        for (int32_t w = 1; w <= n_waves; w++) {
+            int64_t cnt = start[(size_t)w + 1] - start[w];
+            if (cnt == 0) continue;
+            if (scatter == GORSE_B200_SCATTER_ATOMIC) launch_apply<true>(cf, v, d_uij.p + 3 * start[w], cnt, lr, reg);
+            else launch_apply<false>(cf, v, d_uij.p + 3 * start[w], cnt, lr, reg);
+            int32_t st = check();
+            if (st) return done(st);
+        }
+        cudaError_t e2 = cudaStreamSynchronize(c->stream);  // `sorted` dies here
+        if (e2 != cudaSuccess) { set_error("bpr_apply: %s", cudaGetErrorString(e2)); return done(GORSE_B200_ERR_CUDA); }
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("bpr_apply: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    return done(GORSE_B200_OK);
+}
+
+int32_t gorse_b200_bpr_sample_triples(gorse_b200_cf *cf, uint64_t seed, int64_t first_step, int64_t n, int32_t *uij_out)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    GB_CHECK_ARG(n >= 0 && first_step >= 0, "negative n/first_step");
+    if (n == 0) return GORSE_B200_OK;
+    GB_CHECK_ARG(uij_out != nullptr, "uij_out is NULL");
+    if (cf->n_active == 0) { set_error("no user with feedback in this shard"); return GORSE_B200_ERR_STATE; }
+    ScopedDevice sd(cf->ctx->device);
+    gorse_b200_ctx *c = cf->ctx;
+    DevBuf<int32_t> d;
+    GB_TRY(d.alloc((size_t)3 * n));
+    int g = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)c->sm_count * 8));
+    bpr_sample_kernel<<<g, 128, 0, c->stream>>>(make_view(cf), mix64(seed), first_step, n, d.p);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(uij_out, d.p, sizeof(int32_t) * 3 * n, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    d.free();
+    if (e != cudaSuccess) { set_error("bpr_sample: %s", cudaGetErrorString(e)); return GORSE_B200_ERR_CUDA; }
+    return GORSE_B200_OK;
+}
+
+int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_steps, uint64_t seed, int32_t scatter)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    GB_CHECK_ARG(n_steps >= 0, "negative n_steps");
+    GB_CHECK_ARG(scatter == GORSE_B200_SCATTER_STORE || scatter == GORSE_B200_SCATTER_ATOMIC, "bad scatter mode %d", scatter);
+    ScopedDevice sd(cf->ctx->device);
+    gorse_b200_ctx *c = cf->ctx;
+    // rank r runs steps [n*r/W, n*(r+1)/W) of the global step stream on its own user shard
+    int64_t s0 = n_steps * c->rank / c->world, s1 = n_steps * (c->rank + 1) / c->world;
+    if (s1 > s0) {
+        if (cf->n_active == 0) { set_error("no user with feedback in this shard"); return GORSE_B200_ERR_STATE; }
+        BprView v = make_view(cf);
+        if (scatter == GORSE_B200_SCATTER_ATOMIC) launch_epoch<true>(cf, v, s0, s1 - s0, mix64(seed), lr, reg);
+        else launch_epoch<false>(cf, v, s0, s1 - s0, mix64(seed), lr, reg);
+        GB_LAUNCHED(c);
+    }
+    if (c->world > 1) {
+        int64_t n = (int64_t)cf->Q.n;
+        int g = c->sm_count * 8;
+        if (n % 4 == 0) q_delta_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (const float4 *)cf->Q0.p, n / 4);
+        else q_delta_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n);
+        GB_LAUNCHED(c);
+        GB_NCCL_API(nc);
+        GB_NCCL(nc, AllReduce(cf->Q.p, cf->Q.p, (size_t)n, ncclFloat32, ncclSum, c->comm, c->stream));
+        if (n % 4 == 0) q_apply_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (float4 *)cf->Q0.p, n / 4);
+        else q_apply_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n);
+        GB_LAUNCHED(c);
+    }
+    return GORSE_B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,285 @@
+// cf.cu -- CF model state: create/destroy, factor upload/download, normal init, batched Predict.
+#include <algorithm>
+#include <thread>
+
+#include "cf.cuh"
+
+namespace gb {
+
+// N(mean, std) via Box-Muller on the counter RNG; element e of the (users ++ items) stream
+__global__ void init_normal_kernel(float *dst, int64_t n, int64_t stream_off, uint64_t base, float mean, float stddev)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        SStream s;
+        s.x = mix64(base + (uint64_t)(stream_off + i));
+        float u1 = ((float)(s.next32() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float u2 = ((float)(s.next32() >> 8) + 0.5f) * (1.0f / 16777216.0f);
+        float r = sqrtf(-2.0f * logf(u1));
+        float z = r * cospif(2.0f * u2);
+        dst[i] = z * stddev + mean;  // float32(NormFloat64())*stdDev + mean, common/util/random.go:48
+    }
+}
+
+// Predict for d % 16 == 0: one quad per (u, i) pair
+__global__ void predict_quad_kernel(const float *P, const float *Q, int d, int32_t u_lo, const int32_t *users,
+                                    const int32_t *items, int64_t n, float *out)
+{
+    int lane4 = threadIdx.x & 3;
+    unsigned mask = quad_mask();
+    int64_t g = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    int64_t ng = ((int64_t)gridDim.x * blockDim.x) >> 2;
+    for (; g < n; g += ng) {
+        float v = quad_dot_global(P + (int64_t)(users[g] - u_lo) * d, Q + (int64_t)items[g] * d, d / 16, lane4, mask);
+        if (lane4 == 0) out[g] = v;
+    }
+}
+
+__global__ void predict_any_kernel(const float *P, const float *Q, int d, int32_t u_lo, const int32_t *users,
+                                   const int32_t *items, int64_t n, float *out)
+{
+    int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t ng = (int64_t)gridDim.x * blockDim.x;
+    for (; g < n; g += ng) out[g] = dot_any(P + (int64_t)(users[g] - u_lo) * d, Q + (int64_t)items[g] * d, d);
+}
+
+static bool csr_valid(const int64_t *off, int32_t rows, const int32_t *idx, int32_t id_bound, const char *what)
+{
+    if (off[0] != 0) {
+        set_error("%s_off[0] must be 0", what);
+        return false;
+    }
+    for (int32_t r = 0; r < rows; r++)
+        if (off[r + 1] < off[r]) {
+            set_error("%s_off is not non-decreasing at row %d", what, r);
+            return false;
+        }
+    int64_t nnz = off[rows];
+    for (int64_t t = 0; t < nnz; t++)
+        if (idx[t] < 0 || idx[t] >= id_bound) {
+            set_error("%s index %d at position %lld out of range [0, %d)", what, idx[t], (long long)t, id_bound);
+            return false;
+        }
+    return true;
+}
+
+// sort each CSR row ascending (device copy only; sampling i ~ U(R_u) does not depend on the order)
+static void sort_rows(const int64_t *off, int32_t rows, std::vector<int32_t> &idx)
+{
+    unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    if (off[rows] < (1 << 16)) nt = 1;
+    auto work = [&](int32_t r0, int32_t r1) {
+        for (int32_t r = r0; r < r1; r++) {
+            int32_t *b = idx.data() + off[r], *e = idx.data() + off[r + 1];
+            if (!std::is_sorted(b, e)) std::sort(b, e);
+        }
+    };
+    if (nt == 1) {
+        work(0, rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back(work, (int32_t)((int64_t)rows * t / nt), (int32_t)((int64_t)rows * (t + 1) / nt));
+    for (auto &x : th) x.join();
+}
+
+}  // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_items, int32_t n_factors,
+                             const int64_t *user_off, const int32_t *user_items,
+                             const int64_t *item_off, const int32_t *item_users,
+                             gorse_b200_cf **out)
+{
+    GB_CHECK_ARG(ctx != nullptr && out != nullptr, "NULL ctx/out");
+    *out = nullptr;
+    GB_CHECK_ARG(n_users >= 0 && n_items >= 0, "negative table size");
+    GB_CHECK_ARG(n_factors >= 1 && n_factors <= 4096, "n_factors %d out of range [1, 4096]", n_factors);
+    GB_CHECK_ARG(user_off != nullptr, "user_off is NULL");
+    GB_CHECK_ARG(user_off[n_users] == 0 || user_items != nullptr, "user_items is NULL");
+    if (!csr_valid(user_off, n_users, user_items, n_items, "user")) return GORSE_B200_ERR_ARG;
+    bool has_items = item_off != nullptr;
+    if (has_items) {
+        GB_CHECK_ARG(item_off[n_items] == 0 || item_users != nullptr, "item_users is NULL");
+        if (!csr_valid(item_off, n_items, item_users, n_users, "item")) return GORSE_B200_ERR_ARG;
+        GB_CHECK_ARG(item_off[n_items] == user_off[n_users], "user and item CSR disagree on feedback count");
+    }
+    ScopedDevice sd(ctx->device);
+    gorse_b200_cf *cf = new (std::nothrow) gorse_b200_cf();
+    if (!cf) {
+        set_error("host allocation failed");
+        return GORSE_B200_ERR_OOM;
+    }
+    cf->ctx = ctx;
+    cf->n_users = n_users;
+    cf->n_items = n_items;
+    cf->d = n_factors;
+    cf->u_lo = (int32_t)((int64_t)n_users * ctx->rank / ctx->world);
+    cf->u_hi = (int32_t)((int64_t)n_users * (ctx->rank + 1) / ctx->world);
+    cf->n_feedback = user_off[n_users];
+    cf->has_item_csr = has_items;
+    cf->h_user_off.assign(user_off, user_off + n_users + 1);
+    if (has_items) cf->h_item_off.assign(item_off, item_off + n_items + 1);
+
+    int32_t st = GORSE_B200_OK;
+    auto fail = [&](int32_t s) {
+        gorse_b200_cf_destroy(cf);
+        return s;
+    };
+    std::vector<int32_t> sorted(user_items, user_items + cf->n_feedback);
+    sort_rows(user_off, n_users, sorted);
+    std::vector<int32_t> active;
+    for (int32_t u = cf->u_lo; u < cf->u_hi; u++)
+        if (user_off[u + 1] > user_off[u]) active.push_back(u);
+    cf->n_active = (int32_t)active.size();
+
+    int64_t n_local = cf->u_hi - cf->u_lo;
+    if ((st = cf->P.alloc((size_t)n_local * n_factors)) != 0) return fail(st);
+    if ((st = cf->Q.alloc((size_t)n_items * n_factors)) != 0) return fail(st);
+    if (ctx->world > 1 && (st = cf->Q0.alloc((size_t)n_items * n_factors)) != 0) return fail(st);
+    if ((st = cf->user_off.alloc((size_t)n_users + 1)) != 0) return fail(st);
+    if ((st = cf->user_items.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
+    if ((st = cf->active.alloc(active.size())) != 0) return fail(st);
+    cudaStream_t s = ctx->stream;
+    auto up = [&](void *dst, const void *src, size_t bytes) -> int32_t {
+        if (bytes == 0) return GORSE_B200_OK;
+        GB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s));
+        return GORSE_B200_OK;
+    };
+    if ((st = up(cf->user_off.p, user_off, sizeof(int64_t) * ((size_t)n_users + 1))) != 0) return fail(st);
+    if ((st = up(cf->user_items.p, sorted.data(), sizeof(int32_t) * (size_t)cf->n_feedback)) != 0) return fail(st);
+    if ((st = up(cf->active.p, active.data(), sizeof(int32_t) * active.size())) != 0) return fail(st);
+    if (has_items) {
+        if ((st = cf->item_off.alloc((size_t)n_items + 1)) != 0) return fail(st);
+        if ((st = cf->item_users.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
+        if ((st = up(cf->item_off.p, item_off, sizeof(int64_t) * ((size_t)n_items + 1))) != 0) return fail(st);
+        if ((st = up(cf->item_users.p, item_users, sizeof(int32_t) * (size_t)cf->n_feedback)) != 0) return fail(st);
+    }
+    if (cf->P.n) cudaMemsetAsync(cf->P.p, 0, cf->P.n * sizeof(float), s);
+    if (cf->Q.n) cudaMemsetAsync(cf->Q.p, 0, cf->Q.n * sizeof(float), s);
+    cudaError_t e = cudaStreamSynchronize(s);  // host staging vectors die at return
+    if (e != cudaSuccess) {
+        set_error("cf_create: %s", cudaGetErrorString(e));
+        return fail(GORSE_B200_ERR_CUDA);
+    }
+    *out = cf;
+    return GORSE_B200_OK;
+}
+
+int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
+{
+    if (!cf) return GORSE_B200_OK;
+    ScopedDevice sd(cf->ctx->device);
+    cudaStreamSynchronize(cf->ctx->stream);
+    cf->P.free(); cf->Q.free(); cf->Q0.free();
+    cf->user_off.free(); cf->item_off.free();
+    cf->user_items.free(); cf->item_users.free(); cf->active.free();
+    cf->gram.free(); cf->scratch.free();
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 3; b++) cf->als_rows[a][b].free();
+    delete cf;
+    return GORSE_B200_OK;
+}
+
+int32_t gorse_b200_cf_set_factors(gorse_b200_cf *cf, const float *P, const float *Q)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    GB_CHECK_ARG((P != nullptr || cf->n_users == 0) && (Q != nullptr || cf->n_items == 0), "NULL factor table");
+    ScopedDevice sd(cf->ctx->device);
+    cudaStream_t s = cf->ctx->stream;
+    if (cf->P.n)
+        GB_CUDA(cudaMemcpyAsync(cf->P.p, P + (int64_t)cf->u_lo * cf->d, cf->P.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (cf->Q.n) GB_CUDA(cudaMemcpyAsync(cf->Q.p, Q, cf->Q.n * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (cf->Q0.n) GB_CUDA(cudaMemcpyAsync(cf->Q0.p, cf->Q.p, cf->Q.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    return GORSE_B200_OK;
+}
+
+int32_t gorse_b200_cf_get_factors(gorse_b200_cf *cf, float *P, float *Q)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    ScopedDevice sd(cf->ctx->device);
+    cudaStream_t s = cf->ctx->stream;
+    // in a distributed context each rank fills its own user rows of the shared host mirror
+    if (P && cf->P.n)
+        GB_CUDA(cudaMemcpyAsync(P + (int64_t)cf->u_lo * cf->d, cf->P.p, cf->P.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (Q && cf->Q.n) GB_CUDA(cudaMemcpyAsync(Q, cf->Q.p, cf->Q.n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    return GORSE_B200_OK;
+}
+
+int32_t gorse_b200_cf_init_normal(gorse_b200_cf *cf, float mean, float stddev, uint64_t seed)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    ScopedDevice sd(cf->ctx->device);
+    gorse_b200_ctx *c = cf->ctx;
+    uint64_t base = mix64(seed ^ 0x6a09e667f3bcc908ull);
+    // element index in the reference's stream order: users then items (model/cf/model.go:534-535)
+    if (cf->P.n) {
+        init_normal_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(cf->P.p, (int64_t)cf->P.n,
+                                                                  (int64_t)cf->u_lo * cf->d, base, mean, stddev);
+        GB_LAUNCHED(c);
+    }
+    if (cf->Q.n) {
+        init_normal_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(cf->Q.p, (int64_t)cf->Q.n,
+                                                                  (int64_t)cf->n_users * cf->d, base, mean, stddev);
+        GB_LAUNCHED(c);
+    }
+    // every rank generates the same replicated Q; keep the epoch-start copy used by the delta exchange
+    if (cf->Q0.n) GB_CUDA(cudaMemcpyAsync(cf->Q0.p, cf->Q.p, cf->Q.n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    return GORSE_B200_OK;
+}
+
+int32_t gorse_b200_cf_predict(gorse_b200_cf *cf, const int32_t *users, const int32_t *items, int64_t n, float *out)
+{
+    GB_CHECK_ARG(cf != nullptr, "cf is NULL");
+    GB_CHECK_ARG(n >= 0, "negative n");
+    if (n == 0) return GORSE_B200_OK;
+    GB_CHECK_ARG(users && items && out, "NULL argument");
+    for (int64_t t = 0; t < n; t++) {
+        GB_CHECK_ARG(users[t] >= cf->u_lo && users[t] < cf->u_hi, "user %d outside this rank's shard [%d, %d)", users[t],
+                     cf->u_lo, cf->u_hi);
+        GB_CHECK_ARG(items[t] >= 0 && items[t] < cf->n_items, "item %d out of range", items[t]);
+    }
+    ScopedDevice sd(cf->ctx->device);
+    gorse_b200_ctx *c = cf->ctx;
+    DevBuf<int32_t> du, di;
+    DevBuf<float> dout;
+    int32_t st;
+    if ((st = du.alloc(n)) || (st = di.alloc(n)) || (st = dout.alloc(n))) {
+        du.free(); di.free(); dout.free();
+        return st;
+    }
+    auto done = [&](int32_t s) {
+        du.free(); di.free(); dout.free();
+        return s;
+    };
+    cudaError_t e;
+    if ((e = cudaMemcpyAsync(du.p, users, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(di.p, items, n * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream)) != cudaSuccess) {
+        set_error("predict upload: %s", cudaGetErrorString(e));
+        return done(GORSE_B200_ERR_CUDA);
+    }
+    if (cf->d % 16 == 0) {
+        int blocks = std::min<int64_t>(div_up(n * 4, 256), (int64_t)c->sm_count * 16);
+        predict_quad_kernel<<<blocks, 256, 0, c->stream>>>(cf->P.p, cf->Q.p, cf->d, cf->u_lo, du.p, di.p, n, dout.p);
+    } else {
+        int blocks = std::min<int64_t>(div_up(n, 128), (int64_t)c->sm_count * 16);
+        predict_any_kernel<<<blocks, 128, 0, c->stream>>>(cf->P.p, cf->Q.p, cf->d, cf->u_lo, du.p, di.p, n, dout.p);
+    }
+    c->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess ||
+        (e = cudaMemcpyAsync(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
+        set_error("predict: %s", cudaGetErrorString(e));
+        return done(GORSE_B200_ERR_CUDA);
+    }
+    return done(GORSE_B200_OK);
+}
+
+}  // extern "C"

@@ -1,0 +1,28 @@
+// topk.cuh -- brute-force index state shared by topk.cu (exact scan / re-rank) and topk_mma.cu (tcgen05 stage 1).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+struct gorse_b200_index {
+    gorse_b200_ctx *ctx = nullptr;
+    int32_t d = 0, metric = 0;
+    int64_t n = 0, cap = 0;
+    gb::DevBuf<float> X;            // [cap x d] fp32, row-major: the vectors as added (exact re-rank reads these)
+    gb::DevBuf<__nv_bfloat16> Xb;   // [n_pad x d] bf16 mirror feeding the tensor cores (built lazily)
+    gb::DevBuf<float> norm;         // per-vector fp32 norms / error-bound terms (built lazily)
+    bool mma_ready = false;
+    std::mutex mu;
+};
+
+namespace gb {
+
+int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k,
+                     const int32_t *d_cand, const int32_t *d_cand_count, int cand_stride, int32_t *d_idx, float *d_dist,
+                     int32_t *d_count, int prune0, int *d_nan);
+
+bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k);
+int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,
+                   int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan);
+
+}  // namespace gb

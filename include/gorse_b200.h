@@ -1,0 +1,191 @@
+/*
+ * gorse_b200.h -- C ABI of libgorse_b200.so: the B200 (sm_100a) implementation of Gorse's
+ * collaborative-filtering training and brute-force top-k hot path.
+ *
+ * This is exactly what the reference-side cgo shim binds (go/ in this repo):
+ * plain pointers and sizes, no C++/torch types.  Every entry point names the reference
+ * interface it replaces (paths into gorse-io/gorse @ 5404aefa).
+ *
+ * Conventions
+ *   - all pointers are HOST pointers owned by the caller; the library copies during the call and
+ *     never retains them (cgo rule; reference precedent common/blas/blas_openblas.go:24-25)
+ *   - matrices are row-major contiguous fp32; ids are int32; CSR offsets are int64 (len rows+1)
+ *   - every function returns 0 on success, a negative gorse_b200_status otherwise;
+ *     gorse_b200_last_error() gives the message for the calling thread.  Nothing throws or aborts
+ *     across the boundary.
+ *   - there is no CPU fallback: without a CUDA device every call except
+ *     gorse_b200_version/_last_error fails with GORSE_B200_ERR_CUDA.
+ *   - one context = one GPU (+ optionally one rank of an NCCL communicator).  Objects created from
+ *     a context run on its stream; calls on the same object are serialised by the caller
+ *     (cf.Fit runs on one goroutine, master/master.go:457-484) except gorse_b200_index_search*,
+ *     which is thread-safe (ann.Index may be searched concurrently, common/ann/ann_test.go:200-213).
+ */
+#ifndef GORSE_B200_H
+#define GORSE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GORSE_B200_ABI_VERSION 1
+
+typedef enum {
+    GORSE_B200_OK = 0,
+    GORSE_B200_ERR_ARG = -1,      /* bad argument (null, negative size, out-of-range id ...) */
+    GORSE_B200_ERR_CUDA = -2,     /* CUDA runtime/driver error, or no device */
+    GORSE_B200_ERR_NCCL = -3,     /* NCCL error */
+    GORSE_B200_ERR_OOM = -4,      /* device or host allocation failed */
+    GORSE_B200_ERR_RANGE = -5,    /* index out of range (ann.Bruteforce.SearchIndex error, bruteforce.go:41-43) */
+    GORSE_B200_ERR_STATE = -6,    /* call not valid in the object's current state */
+    GORSE_B200_ERR_UNSUPPORTED = -7
+} gorse_b200_status;
+
+typedef struct gorse_b200_ctx gorse_b200_ctx;     /* one GPU, one stream, optional NCCL rank */
+typedef struct gorse_b200_cf gorse_b200_cf;       /* factor tables + feedback CSR resident in HBM */
+typedef struct gorse_b200_index gorse_b200_index; /* brute-force vector index resident in HBM */
+
+int32_t gorse_b200_version(void);
+const char *gorse_b200_last_error(void); /* thread-local, never NULL */
+
+/* ------------------------------------------------------------------------------------------
+ * Context.  Replaces: common/parallel.Parallel (common/parallel/parallel.go:33-94), the
+ * reference's data-parallel scheduler for Fit -- a kernel launch on the context's stream.
+ * ---------------------------------------------------------------------------------------- */
+int32_t gorse_b200_device_count(int32_t *count);
+int32_t gorse_b200_ctx_create(int32_t device, gorse_b200_ctx **out);
+/* multi-GPU: one context per GPU, rank in [0, world).  nccl_id = GORSE_B200_NCCL_ID_BYTES bytes
+ * produced by gorse_b200_nccl_unique_id() on rank 0 and carried to the other ranks by the host
+ * (gRPC between Gorse nodes, torch.distributed in bench.py).  Collective: all ranks must call. */
+#define GORSE_B200_NCCL_ID_BYTES 128
+int32_t gorse_b200_nccl_unique_id(void *id_out);
+int32_t gorse_b200_ctx_create_dist(int32_t device, int32_t rank, int32_t world, const void *nccl_id,
+                                   gorse_b200_ctx **out);
+int32_t gorse_b200_ctx_destroy(gorse_b200_ctx *ctx);
+int32_t gorse_b200_ctx_sync(gorse_b200_ctx *ctx);
+int32_t gorse_b200_ctx_rank(const gorse_b200_ctx *ctx, int32_t *rank, int32_t *world);
+/* measurement hooks (bench.py): CUDA events on the context's own stream, and the number of this
+ * library's kernels launched on it so far */
+int32_t gorse_b200_ctx_timer_begin(gorse_b200_ctx *ctx);
+int32_t gorse_b200_ctx_timer_end(gorse_b200_ctx *ctx, float *ms_out); /* records, syncs, returns elapsed */
+int32_t gorse_b200_ctx_launch_count(const gorse_b200_ctx *ctx, int64_t *count);
+int32_t gorse_b200_ctx_flush_l2(gorse_b200_ctx *ctx); /* writes a buffer larger than L2 */
+int32_t gorse_b200_ctx_barrier(gorse_b200_ctx *ctx);  /* NCCL barrier across ranks (no-op for world 1) */
+/* page-locked host memory for the shim's flat factor mirror (SURVEY 8b "ownership"): factor uploads and
+ * downloads from it run at full PCIe rate.  Plain host pointers work everywhere too, just slower. */
+int32_t gorse_b200_host_alloc(size_t bytes, void **out);
+int32_t gorse_b200_host_free(void *p);
+
+/* ------------------------------------------------------------------------------------------
+ * CF model state.  Replaces cf.BaseMatrixFactorization's UserFactor/ItemFactor ([][]float32,
+ * model/cf/model.go:118-127) and the dataset.CFSplit accessors GetUserFeedback/GetItemFeedback
+ * (dataset/dataset.go:40-60) flattened to CSR by the shim.
+ *
+ * user_off[n_users+1], user_items[user_off[n_users]] : R_u  (any order, duplicates allowed; the
+ *     device copy is sorted per row for the negative-sampling membership test)
+ * item_off[n_items+1], item_users[...]               : R_i  (may be NULL when ALS is not used)
+ * In a distributed context every rank passes the FULL CSR; rank r trains users
+ * [r*U/world, (r+1)*U/world) and owns those rows of P; Q is replicated.
+ * ---------------------------------------------------------------------------------------- */
+int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_items, int32_t n_factors,
+                             const int64_t *user_off, const int32_t *user_items,
+                             const int64_t *item_off, const int32_t *item_users,
+                             gorse_b200_cf **out);
+int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf);
+/* warm start / parity mode: upload full tables (P: n_users x d, Q: n_items x d) */
+int32_t gorse_b200_cf_set_factors(gorse_b200_cf *cf, const float *P, const float *Q);
+/* BPR.Init / ALS.Init (model/cf/model.go:532-540, 598-606 -> util.NormalMatrix,
+ * common/util/random.go:54-60): i.i.d. N(mean, std) rows, users then items.  The Go math/rand
+ * stream is not reproducible; the distribution is. */
+int32_t gorse_b200_cf_init_normal(gorse_b200_cf *cf, float mean, float stddev, uint64_t seed);
+/* host mirror fill: GetUserFactor/GetItemFactor reads (master/tasks.go:946,969) are served from it */
+int32_t gorse_b200_cf_get_factors(gorse_b200_cf *cf, float *P, float *Q);
+/* Predict / internalPredict (model/cf/model.go:182-203) for a batch of (user, item) index pairs;
+ * floats.Dot summation order (AVX-512 tree), bit-equal to the host mirror */
+int32_t gorse_b200_cf_predict(gorse_b200_cf *cf, const int32_t *users, const int32_t *items, int64_t n,
+                              float *out);
+
+/* ------------------------------------------------------------------------------------------
+ * BPR.  Replaces the body of BPR.Fit's epoch loop, model/cf/model.go:448-490.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {
+    /* racy read-modify-write exactly like the reference's lock-free goroutines: new row =
+     * fma(t, lr, row as read by this step).  Bit-exact vs the oracle when the triples of one launch
+     * touch disjoint rows. */
+    GORSE_B200_SCATTER_STORE = 0,
+    /* Hogwild with vectorised atomics (red.global.add.v4.f32): no update is ever lost */
+    GORSE_B200_SCATTER_ATOMIC = 1
+} gorse_b200_scatter;
+
+typedef enum {
+    GORSE_B200_ORDER_HOGWILD = 0,   /* all triples in one launch, like Jobs = many */
+    /* the host splits the list into conflict-free waves and launches them in order: identical to the
+     * reference with Jobs = 1 on this triple stream (bit-exact with SCATTER_STORE) */
+    GORSE_B200_ORDER_SEQUENTIAL = 1
+} gorse_b200_order;
+
+/* apply an explicit list of n (u, i, j) triples (uij[3n]); a triple with j < 0 is skipped */
+int32_t gorse_b200_bpr_apply_triples(gorse_b200_cf *cf, const int32_t *uij, int64_t n, float lr, float reg,
+                                     int32_t scatter, int32_t order);
+/* the triples gorse_b200_bpr_epoch(seed) samples for steps [first_step, first_step + n):
+ * u uniform over users with feedback, i uniform in R_u, j uniform over items rejected while in R_u
+ * (model/cf/model.go:449-468).  A user whose row covers every item yields j = -1. */
+int32_t gorse_b200_bpr_sample_triples(gorse_b200_cf *cf, uint64_t seed, int64_t first_step, int64_t n,
+                                      int32_t *uij_out);
+/* one epoch = n_steps fused sample-gather-dot-sigmoid-scatter steps in ONE kernel launch
+ * (n_steps = trainSet.CountFeedback(), model/cf/model.go:448).  In a distributed context each
+ * rank runs n_steps/world steps on its user shard, then item-factor deltas are all-reduced. */
+int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_steps, uint64_t seed,
+                             int32_t scatter);
+
+/* ------------------------------------------------------------------------------------------
+ * ALS / eALS ("CCD").  Replaces one iteration of ALS.Fit's epoch loop, model/cf/model.go:641-738
+ * (Gram S^q, user rows, Gram S^p, item rows).  Needs item_off/item_users at create time.
+ * ---------------------------------------------------------------------------------------- */
+int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alpha);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluate.  Replaces cf.Evaluate (model/cf/evaluator.go:35-72) with scorers NDCG, Precision,
+ * Recall at topk.  test CSR: test positives per user; neg CSR: sampled negatives per user
+ * (dataset.SampleUserNegatives, dataset/dataset.go:242-256 -- sampled by the caller).
+ * out[3] = {NDCG, Precision, Recall}.
+ * ---------------------------------------------------------------------------------------- */
+int32_t gorse_b200_cf_evaluate(gorse_b200_cf *cf, const int64_t *test_off, const int32_t *test_items,
+                               const int64_t *neg_off, const int32_t *neg_items, int32_t topk,
+                               float *out);
+
+/* ------------------------------------------------------------------------------------------
+ * Brute-force index.  Replaces ann.Bruteforce[[]float32] (common/ann/bruteforce.go:24-83)
+ * behind ann.Index (common/ann/ann.go:21-25).
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {
+    GORSE_B200_METRIC_EUCLIDEAN = 0, /* floats.Euclidean (common/ann/ann_test.go:126) */
+    GORSE_B200_METRIC_NEG_DOT = 1    /* -floats.Dot (logics/cf.go:32-34) */
+} gorse_b200_metric;
+
+int32_t gorse_b200_index_create(gorse_b200_ctx *ctx, int32_t dim, int32_t metric, gorse_b200_index **out);
+int32_t gorse_b200_index_destroy(gorse_b200_index *ix);
+/* Bruteforce.Add (bruteforce.go:33-37) for n vectors at once; *count_out = len after append
+ * (the reference returns the 1-based length) */
+int32_t gorse_b200_index_add(gorse_b200_index *ix, const float *vectors, int64_t n, int64_t *count_out);
+int32_t gorse_b200_index_len(const gorse_b200_index *ix, int64_t *count_out);
+/* SearchVector (bruteforce.go:65-83) for nq query vectors; results ascending by distance.
+ * idx_out/dist_out: nq x k, rows padded with idx = -1; count_out[nq] = results per query
+ * (fewer than k when the index is small or prune0 dropped score <= 0). */
+int32_t gorse_b200_index_search_vectors(gorse_b200_index *ix, const float *queries, int64_t nq, int32_t k,
+                                        int32_t prune0, int32_t *idx_out, float *dist_out, int32_t *count_out);
+/* SearchIndex (bruteforce.go:39-63) for nq stored vectors q_idx[nq]; never returns the query itself;
+ * GORSE_B200_ERR_RANGE if any index is out of range */
+int32_t gorse_b200_index_search_indices(gorse_b200_index *ix, const int64_t *q_idx, int64_t nq, int32_t k,
+                                        int32_t prune0, int32_t *idx_out, float *dist_out, int32_t *count_out);
+/* all-pairs SearchIndex for stored vectors [q0, q1): item-to-item / user-to-user neighbours
+ * (what logics.item_to_item asks its vector store for, logics/item_to_item.go:50-62) */
+int32_t gorse_b200_index_search_range(gorse_b200_index *ix, int64_t q0, int64_t q1, int32_t k, int32_t prune0,
+                                      int32_t *idx_out, float *dist_out, int32_t *count_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GORSE_B200_H */

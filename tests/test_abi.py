@@ -1,0 +1,90 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/gorse_b200.h
+declares, and fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gorse_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gorse_b200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(gb):
+    from gorse_b200 import _lib
+
+    syms = header_symbols()
+    assert len(syms) >= 30
+    raw = C.CDLL(_lib.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"{s} declared in include/gorse_b200.h but not exported"
+    assert set(syms) == set(_lib.PROTOTYPES), set(syms) ^ set(_lib.PROTOTYPES)
+    assert _lib.lib.gorse_b200_version() == 1
+
+
+def test_only_sm100a_code_in_library(gb):
+    import shutil
+    import subprocess
+
+    from gorse_b200 import _lib
+
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not on PATH")
+    out = subprocess.run(["cuobjdump", "-lelf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_product_never_touches_the_oracle():
+    # the oracle is test infrastructure: nothing under gorse_b200/ may import, link or dlopen it
+    bad = []
+    for dp, _, files in os.walk(os.path.join(ROOT, "gorse_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                if re.search(r"import oracle|from oracle|gbo_|libgorse_oracle|oracle/", txt):
+                    bad.append(os.path.join(dp, f))
+    assert not bad, bad
+
+
+def test_no_cpu_fallback_without_a_device(gb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is exercised on the CPU box")
+    with pytest.raises(gb.GorseB200Error) as ei:
+        gb.Context(0)
+    assert ei.value.status == -2  # GORSE_B200_ERR_CUDA
+    assert ei.value.message
+
+
+def test_argument_errors_do_not_need_a_device(gb):
+    from gorse_b200 import _lib
+
+    h = C.c_void_p()
+    assert _lib.lib.gorse_b200_cf_create(None, 1, 1, 8, None, None, None, None, C.byref(h)) == _lib.ERR_ARG
+    assert b"NULL" in _lib.lib.gorse_b200_last_error()
+    assert _lib.lib.gorse_b200_index_create(None, 8, 1, C.byref(h)) == _lib.ERR_ARG
+    assert _lib.lib.gorse_b200_ctx_sync(None) == _lib.ERR_ARG
+
+
+def test_synth_shapes(gb):
+    from gorse_b200 import synth
+
+    off, items = synth.make_feedback(500, 200, 5000, seed=1)
+    assert off[0] == 0 and off[-1] == items.size and np.all(np.diff(off) >= 1)
+    for u in range(0, 500, 37):
+        row = items[off[u]:off[u + 1]]
+        assert np.all(np.diff(row) > 0) and row.min() >= 0 and row.max() < 200
+    (tro, tri), (teo, tei) = synth.leave_one_out(off, items, seed=2)
+    assert tro[-1] + teo[-1] == off[-1] and teo[-1] == 500
+    no, ni = synth.sample_negatives(200, (tro, tri), (teo, tei), 20, seed=3)
+    assert no[-1] == 500 * 20
+    t = synth.conflict_free_triples(off, items, 200, 40, seed=4)
+    assert len(set(t[:, 0])) == len(t) and len(set(t[:, 1]) | set(t[:, 2])) == 2 * len(t)
