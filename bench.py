@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's headline metric on its headline config.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c5|c1] [--small]
+
+A "step" is one BPR epoch = |R| fused sample-gather-dot-sigmoid-scatter triples in ONE kernel launch on
+synthetic data of BASELINE config #2 (1M users x 100K items x 10M feedback, d=64).  For N > 1 (torchrun, one
+rank per GPU) the workload is weak-scaled: every rank owns 1M users / 10M feedback, the item table is
+replicated and its deltas are all-reduced (NCCL) once per epoch.
+
+One JSON line on rank 0; see DESIGN.md "measurement" for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (users per rank, items, feedback per rank, d, description)
+    "c2": (1_000_000, 100_000, 10_000_000, 64, "BPR 1M users x 100K items x 10M feedback, d=64 (BASELINE configs[1])"),
+    "c5": (1_250_000, 1_000_000, 25_000_000, 128, "BPR 10M x 1M x 200M, d=128 split over 8 ranks (BASELINE configs[4] per-rank share)"),
+    "c1": (943, 1_682, 100_000, 16, "BPR ml-100k-shaped surrogate, d=16 (BASELINE configs[0])"),
+    "small": (50_000, 10_000, 500_000, 64, "reduced smoke size (NOT a bench number)"),
+}
+LR, REG = 0.05, 0.01            # BPR defaults, model/cf/model.go:391-392
+INIT_STD = 0.001                # :394
+E2E_EPOCHS = 100                # BPR default NEpochs, model/cf/model.go:390
+ZIPF_S = 1.0                    # item popularity skew of the synthetic feedback
+_CPU_CACHE = {}
+
+
+def bytes_per_triple(d):
+    return 6 * d * 4 + 12       # 3 rows read + 3 rows written + 3 ids
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        if not rows:
+            return None
+        sm = sorted(float(r[0]) for r in rows)
+        reasons = [n for k, n in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap"))
+                   if any(r[k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+_DATA_CACHE = {}
+
+
+def get_data(wl, seed):
+    from gorse_b200 import synth
+
+    if (wl, seed) not in _DATA_CACHE:
+        upr, n_items, fpr, d, _ = WORKLOADS[wl]
+        _DATA_CACHE[(wl, seed)] = synth.make_feedback(upr, n_items, fpr, seed=seed, zipf_s=ZIPF_S, exact=True)
+    return _DATA_CACHE[(wl, seed)]
+
+
+def make_shard(wl, rank, world):
+    """This rank's users (seeded per rank) inside a global CSR whose other rows are empty: BPR touches only the
+    rank's own user shard, so the other shards' rows are never read (see DESIGN.md multi-GPU)."""
+    from gorse_b200 import synth
+
+    upr, n_items, fpr, d, _ = WORKLOADS[wl]
+    off_l, items = get_data(wl, 1000 + rank)
+    n_users = upr * world
+    off = np.zeros(n_users + 1, np.int64)
+    lo = rank * upr
+    off[lo:lo + upr + 1] = off_l
+    off[lo + upr + 1:] = off_l[-1]
+    return n_users, n_items, d, off, items
+
+
+def cpu_baseline(wl, seconds_budget=3.0, prefer_ref=True):
+    """The reference's CPU path for the same step on this box's host cores: per triple the reference's own call
+    sequence (2x dot, exp, 3 row copies, 10 vector ops, model/cf/model.go:469-488) through the reference's C kernels
+    (oracle/_ref, compiled from /root/reference/common/floats/src) when they are present and the CPU has AVX-512,
+    else through the oracle port; Hogwild over all host cores.  Bounded sample of the workload's step."""
+    import oracle
+    from gorse_b200 import synth
+
+    upr, n_items, fpr, d, _ = WORKLOADS[wl]
+    if wl not in _CPU_CACHE:
+        off, items = get_data(wl, 1000)
+        rng = np.random.default_rng(0)
+        P = (rng.standard_normal((upr, d)) * INIT_STD).astype(np.float32)
+        Q = (rng.standard_normal((n_items, d)) * INIT_STD).astype(np.float32)
+        _CPU_CACHE[wl] = (off, items, P, Q, np.nonzero(np.diff(off) > 0)[0].astype(np.int32))
+    off, items, P, Q, active = _CPU_CACHE[wl]
+    cores = len(os.sched_getaffinity(0))
+    kind = "port"
+    use_ref = False
+    if prefer_ref and oracle.ref_available() and "avx512f" in open("/proc/cpuinfo").read() and oracle.ref_bind():
+        kind, use_ref = "reference", True
+    probe = 200_000
+    sec = oracle.bpr_epoch_threads(P, Q, off, items, active, 1, probe, LR, REG, cores, use_ref)
+    n = int(min(off[-1] * 4, max(probe, probe * seconds_budget / max(sec, 1e-6))))
+    sec = oracle.bpr_epoch_threads(P, Q, off, items, active, 2, n, LR, REG, cores, use_ref)
+    return {"value": n / sec, "unit": "triples/s", "cores": cores, "kind": kind,
+            "sample": f"{n} sampled triples of the {WORKLOADS[wl][4]} step, Hogwild over {cores} threads, {sec:.2f} s wall"}, n, sec
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    wl = args.workload
+    upr, n_items, fpr, d, desc = WORKLOADS[wl]
+    times, vals, last = [], [], None
+    for s in range(args.warmup + args.steps):
+        cb, n, sec = cpu_baseline(wl, seconds_budget=2.0)
+        if s >= args.warmup:
+            times.append(sec)
+            vals.append(cb["value"])
+        last = cb
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {"impl": "reference", "metric": "BPR-MF triples/sec", "value": v, "unit": "triples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "users": upr, "items": n_items, "feedback": fpr, "d": d, "lr": LR, "reg": REG,
+                       "step": "bounded sample of one epoch on host cores"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    rank, world, local = dist_env()
+    assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    dist = None
+    if world > 1:
+        import torch  # control plane only: rendezvous, id broadcast, max-over-ranks
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    import gorse_b200 as gb
+
+    wl = args.workload
+    upr, n_items_w, fpr, d, desc = WORKLOADS[wl]
+    n_users, n_items, d, off, items = make_shard(wl, rank, world)
+    n_local = int(off[-1])
+    if world > 1:
+        import torch
+
+        cnt = torch.tensor([n_local], dtype=torch.int64)
+        allc = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(allc, cnt)
+        # every rank runs the same number of steps per epoch (the global step stream is split evenly)
+        steps_per_epoch = int(min(int(c.item()) for c in allc)) * world
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            idbuf = torch.frombuffer(bytearray(gb.nccl_unique_id()), dtype=torch.uint8).clone()
+        dist.broadcast(idbuf, 0)
+        ctx = gb.Context(local, rank, world, bytes(idbuf.numpy().tobytes()))
+    else:
+        steps_per_epoch = n_local
+        ctx = gb.Context(local)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        import torch
+
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    model = gb.CFModel(ctx, n_users, n_items, d, off, items)
+    model.init_normal(0.0, INIT_STD, 0)
+    ctx.sync()
+    scatter = gb.SCATTER_ATOMIC if args.scatter == "atomic" else gb.SCATTER_STORE
+
+    # ---- device-resident timing: K epochs, CUDA events on the library's own stream, max over ranks ----
+    for w in range(args.warmup):
+        model.bpr_epoch(LR, REG, steps_per_epoch, 100 + w, scatter)
+    ctx.barrier()
+    if dist:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ctx.launch_count()
+    t0 = time.time()
+    ctx.timer_begin()
+    for s in range(args.steps):
+        model.bpr_epoch(LR, REG, steps_per_epoch, 1000 + s, scatter)
+    ctx.barrier() if world > 1 else None
+    ms_total = ctx.timer_end()
+    t1 = time.time()
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    ms_total = max_over_ranks(ms_total)
+    ms_per_step = ms_total / args.steps
+    value = steps_per_epoch / (ms_per_step * 1e-3)
+
+    # ---- the dominant kernel alone (one epoch launch per event pair), for the roofline ----
+    kms = []
+    for s in range(min(args.steps, 5)):
+        ctx.timer_begin()
+        model.bpr_epoch(LR, REG, steps_per_epoch, 2000 + s, scatter)  # N > 1: includes the delta exchange
+        kms.append(ctx.timer_end())
+    k_ms = float(np.mean(kms))
+    peak, peak_src = read_peaks()
+    per_launch_triples = steps_per_epoch / world
+    achieved = bytes_per_triple(d) * per_launch_triples / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "bpr_epoch_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(f"{wl}_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": f"bpr_epoch_kernel<{d // 16 if d % 16 == 0 else 0},{args.scatter}>",
+                "kernel_ms": k_ms, "algorithmic_bytes_per_launch": bytes_per_triple(d) * per_launch_triples,
+                "peak_source": peak_src}
+
+    # ---- end to end through the C-ABI with HOST buffers: what cf.BPR.Fit does per call ----
+    # create (CSR H2D) + factor upload from the pinned mirror + E2E_EPOCHS epochs + factor download, all timed
+    e2e = None
+    if not args.no_e2e:
+        hp = gb.PinnedArray((n_users, d))
+        hq = gb.PinnedArray((n_items, d))
+        rng = np.random.default_rng(1)
+        lo, hi = rank * upr, (rank + 1) * upr
+        hp.array[lo:hi] = (rng.standard_normal((upr, d)) * INIT_STD).astype(np.float32)
+        hq.array[:] = (np.random.default_rng(2).standard_normal((n_items, d)) * INIT_STD).astype(np.float32)
+        e_epochs = max(1, args.e2e_epochs)
+        model.close()
+        if dist:
+            dist.barrier()
+        w0 = time.time()
+        m2 = gb.CFModel(ctx, n_users, n_items, d, off, items)
+        m2.set_factors(hp.array, hq.array)
+        for s in range(e_epochs):
+            m2.bpr_epoch(LR, REG, steps_per_epoch, 3000 + s, scatter)
+        m2.get_factors(hp.array, hq.array)
+        w1 = time.time()
+        e_sec = max_over_ranks(w1 - w0)
+        assert np.isfinite(hq.array).all()
+        h2d = (off.nbytes + items.nbytes + upr * d * 4 + n_items * d * 4)
+        d2h = upr * d * 4 + n_items * d * 4
+        e2e = {"value": e_epochs * steps_per_epoch / e_sec, "unit": "triples/s",
+               "h2d_bytes_per_step": h2d / e_epochs, "d2h_bytes_per_step": d2h / e_epochs,
+               "what": f"one Fit-shaped call per rank: cf_create (CSR upload) + set_factors from the pinned mirror + {e_epochs} epochs "
+                       f"(reference default NEpochs) + get_factors; bytes are per epoch, amortised over the call",
+               "wall_s": e_sec}
+        m2.close()
+        hp.free()
+        hq.free()
+    else:
+        model.close()
+
+    line = None
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu:
+            cb, _, _ = cpu_baseline(wl)
+        line = {"metric": "BPR-MF triples/sec", "value": value, "unit": "triples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc + (f" per rank x {world} ranks (weak scaling; Q replicated, per-epoch NCCL all-reduce of item deltas)" if world > 1 else ""),
+                           "users": n_users, "items": n_items, "feedback_per_epoch": steps_per_epoch, "d": d, "lr": LR, "reg": REG,
+                           "item_popularity": f"zipf({ZIPF_S})", "scatter": args.scatter,
+                           "cache": "user table (256 MB/rank at c2) is larger than L2 (126 MB); the item table is meant to stay L2-resident; no flush between steps"},
+                "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scatter", default="atomic", choices=["atomic", "store"])
+    ap.add_argument("--e2e-epochs", type=int, default=E2E_EPOCHS)
+    ap.add_argument("--zipf", type=float, default=None, help="item popularity exponent of the synthetic data (default 1.0; 0 = uniform)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.zipf is not None:
+        global ZIPF_S
+        ZIPF_S = args.zipf
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

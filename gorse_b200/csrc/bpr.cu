@@ -12,9 +12,9 @@ namespace gb {
 
 struct BprView {
     float *P, *Q;
-    const int64_t *user_off;
+    const UserMeta *meta;       // per user: row offset, length, 64-bit Bloom signature of the row (one 16-byte load)
     const int32_t *user_items;
-    const int32_t *active;
+    const int32_t *active;      // nullptr when every user of the shard has feedback (active[k] == u_lo + k)
     int32_t n_active, n_items, d, u_lo;
 };
 
@@ -44,18 +44,31 @@ __device__ __forceinline__ float bpr_grad(float diff)
     return __fdiv_rn(e, __fadd_rn(1.0f, e));
 }
 
-// one SGD step by a quad, rows held in registers.  C = d / 16 chunks.
-template <int C, bool ATOMIC>
-__device__ __forceinline__ void bpr_step_quad(float *Pu, float *Qi, float *Qj, int lane4, unsigned mask, float lr, float reg)
-{
+// the three rows of one triple, register resident (C = d / 16 chunks per lane)
+template <int C>
+struct Rows {
     float4 p[C], qi[C], qj[C];
+};
+
+template <int C>
+__device__ __forceinline__ void load_rows(Rows<C> &r, const float *Pu, const float *Qi, const float *Qj, int lane4)
+{
     Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
 #pragma unroll
-    for (int c = 0; c < C; c++) p[c] = ld_row(Pu + 16 * c);
+    for (int c = 0; c < C; c++) r.p[c] = ld_row(Pu + 16 * c);
 #pragma unroll
-    for (int c = 0; c < C; c++) qi[c] = ld_row(Qi + 16 * c);
+    for (int c = 0; c < C; c++) r.qi[c] = ld_row(Qi + 16 * c);
 #pragma unroll
-    for (int c = 0; c < C; c++) qj[c] = ld_row(Qj + 16 * c);
+    for (int c = 0; c < C; c++) r.qj[c] = ld_row(Qj + 16 * c);
+}
+
+// one SGD step by a quad on rows already in registers
+template <int C, bool ATOMIC>
+__device__ __forceinline__ void bpr_step_rows(const Rows<C> &r, float *Pu, float *Qi, float *Qj, int lane4, unsigned mask,
+                                              float lr, float reg)
+{
+    const float4 *p = r.p, *qi = r.qi, *qj = r.qj;
+    Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
     float4 ai = make_float4(0.f, 0.f, 0.f, 0.f), aj = ai;
 #pragma unroll
     for (int c = 0; c < C; c++) {
@@ -80,6 +93,14 @@ __device__ __forceinline__ void bpr_step_quad(float *Pu, float *Qi, float *Qj, i
         if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Pu + 16 * c, o); }
         else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(p[c], k_))); st_row(Pu + 16 * c, o); }
     }
+}
+
+template <int C, bool ATOMIC>
+__device__ __forceinline__ void bpr_step_quad(float *Pu, float *Qi, float *Qj, int lane4, unsigned mask, float lr, float reg)
+{
+    Rows<C> r;
+    load_rows<C>(r, Pu, Qi, Qj, lane4);
+    bpr_step_rows<C, ATOMIC>(r, Pu, Qi, Qj, lane4, mask, lr, reg);
 }
 
 // same step for any d % 16 == 0 without register-resident rows (two passes over L2-hot rows)
@@ -141,14 +162,18 @@ __device__ __forceinline__ void sample_triple(const BprView &v, uint64_t base, i
 {
     SStream s;
     s.x = mix64(base + (uint64_t)step);
-    u = __ldg(v.active + s.bounded((uint32_t)v.n_active));
-    int64_t o = __ldg(v.user_off + u), len = __ldg(v.user_off + u + 1) - o;
+    uint32_t ua = s.bounded((uint32_t)v.n_active);
+    u = v.active ? __ldg(v.active + ua) : v.u_lo + (int32_t)ua;
+    const UserMeta m = ld_meta(v.meta + u);
+    const int64_t o = m.off();
+    const int64_t len = m.len();
     i = __ldg(v.user_items + o + s.bounded((uint32_t)len));
     j = -1;
     if (len < v.n_items) {
         for (;;) {
             int32_t c = (int32_t)s.bounded((uint32_t)v.n_items);
-            if (!row_contains(v.user_items + o, len, c)) { j = c; break; }
+            // the Bloom signature answers "certainly not in R_u" for most candidates without touching the row
+            if (!m.maybe_contains(c) || !row_contains(v.user_items + o, len, c)) { j = c; break; }
         }
     }
 }
@@ -161,12 +186,31 @@ __global__ void __launch_bounds__(256) bpr_epoch_kernel(BprView v, int64_t step0
     const unsigned mask = quad_mask();
     int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
     const int64_t nq = ((int64_t)gridDim.x * blockDim.x) >> 2;
-    for (; q < n_steps; q += nq) {
-        int32_t u, i, j;
-        sample_triple(v, base, step0 + q, u, i, j);
-        if (j < 0) continue;
-        bpr_step_dispatch<C, ATOMIC>(v.P + (int64_t)(u - v.u_lo) * v.d, v.Q + (int64_t)i * v.d, v.Q + (int64_t)j * v.d,
-                                     v.d, lane4, mask, lr, reg);
+    if (C > 0) {
+        // software pipeline: the row gathers of step k are in flight while step k+1 is being sampled
+        // (its own chain of 2-3 dependent index loads), so one iteration costs one memory round trip
+        constexpr int CC = C > 0 ? C : 1;
+        int32_t u = 0, i = 0, j = -1;
+        if (q < n_steps) sample_triple(v, base, step0 + q, u, i, j);
+        while (q < n_steps) {
+            Rows<CC> r;
+            float *Pu = v.P + (int64_t)(u - v.u_lo) * v.d, *Qi = v.Q + (int64_t)i * v.d, *Qj = v.Q + (int64_t)j * v.d;
+            const bool live = j >= 0;
+            if (live) load_rows<CC>(r, Pu, Qi, Qj, lane4);
+            const int64_t qn = q + nq;
+            int32_t un = 0, in = 0, jn = -1;
+            if (qn < n_steps) sample_triple(v, base, step0 + qn, un, in, jn);
+            if (live) bpr_step_rows<CC, ATOMIC>(r, Pu, Qi, Qj, lane4, mask, lr, reg);
+            q = qn; u = un; i = in; j = jn;
+        }
+    } else {
+        for (; q < n_steps; q += nq) {
+            int32_t u, i, j;
+            sample_triple(v, base, step0 + q, u, i, j);
+            if (j < 0) continue;
+            bpr_step_dispatch<C, ATOMIC>(v.P + (int64_t)(u - v.u_lo) * v.d, v.Q + (int64_t)i * v.d, v.Q + (int64_t)j * v.d,
+                                         v.d, lane4, mask, lr, reg);
+        }
     }
 }
 
@@ -255,7 +299,8 @@ static BprView make_view(gorse_b200_cf *cf)
 {
     BprView v;
     v.P = cf->P.p; v.Q = cf->Q.p;
-    v.user_off = cf->user_off.p; v.user_items = cf->user_items.p; v.active = cf->active.p;
+    v.meta = cf->user_meta.p; v.user_items = cf->user_items.p;
+    v.active = cf->all_active ? nullptr : cf->active.p;
     v.n_active = cf->n_active; v.n_items = cf->n_items; v.d = cf->d; v.u_lo = cf->u_lo;
     return v;
 }

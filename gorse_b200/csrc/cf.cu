@@ -137,6 +137,17 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     for (int32_t u = cf->u_lo; u < cf->u_hi; u++)
         if (user_off[u + 1] > user_off[u]) active.push_back(u);
     cf->n_active = (int32_t)active.size();
+    cf->all_active = cf->n_active == cf->u_hi - cf->u_lo;
+    if (cf->n_feedback >= (1ll << 38)) { set_error("more than 2^38 feedback entries are not supported"); return fail(GORSE_B200_ERR_UNSUPPORTED); }
+    std::vector<UserMeta> meta((size_t)n_users);
+    for (int32_t u = 0; u < n_users; u++) {
+        int64_t o = user_off[u], len = user_off[u + 1] - o;
+        if (len >= (1ll << 26)) { set_error("user %d has more than 2^26 feedback entries", u); return fail(GORSE_B200_ERR_UNSUPPORTED); }
+        uint64_t bloom = 0;
+        for (int64_t t = 0; t < len; t++) bloom |= UserMeta::bit(sorted[(size_t)(o + t)]);
+        meta[u].off_len = (uint64_t)o | ((uint64_t)len << 38);
+        meta[u].bloom = bloom;
+    }
 
     int64_t n_local = cf->u_hi - cf->u_lo;
     if ((st = cf->P.alloc((size_t)n_local * n_factors)) != 0) return fail(st);
@@ -145,6 +156,7 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     if ((st = cf->user_off.alloc((size_t)n_users + 1)) != 0) return fail(st);
     if ((st = cf->user_items.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
     if ((st = cf->active.alloc(active.size())) != 0) return fail(st);
+    if ((st = cf->user_meta.alloc((size_t)n_users)) != 0) return fail(st);
     cudaStream_t s = ctx->stream;
     auto up = [&](void *dst, const void *src, size_t bytes) -> int32_t {
         if (bytes == 0) return GORSE_B200_OK;
@@ -154,6 +166,7 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     if ((st = up(cf->user_off.p, user_off, sizeof(int64_t) * ((size_t)n_users + 1))) != 0) return fail(st);
     if ((st = up(cf->user_items.p, sorted.data(), sizeof(int32_t) * (size_t)cf->n_feedback)) != 0) return fail(st);
     if ((st = up(cf->active.p, active.data(), sizeof(int32_t) * active.size())) != 0) return fail(st);
+    if ((st = up(cf->user_meta.p, meta.data(), sizeof(UserMeta) * meta.size())) != 0) return fail(st);
     if (has_items) {
         if ((st = cf->item_off.alloc((size_t)n_items + 1)) != 0) return fail(st);
         if ((st = cf->item_users.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
@@ -178,7 +191,7 @@ int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
     cudaStreamSynchronize(cf->ctx->stream);
     cf->P.free(); cf->Q.free(); cf->Q0.free();
     cf->user_off.free(); cf->item_off.free();
-    cf->user_items.free(); cf->item_users.free(); cf->active.free();
+    cf->user_items.free(); cf->item_users.free(); cf->active.free(); cf->user_meta.free();
     cf->gram.free(); cf->scratch.free();
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 3; b++) cf->als_rows[a][b].free();

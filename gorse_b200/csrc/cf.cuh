@@ -17,6 +17,19 @@
 #pragma once
 #include "common.cuh"
 
+namespace gb {
+// Per-user sampling record: one 16-byte load gives the row's offset and length and a 64-bit Bloom signature
+// (one hash) used to answer "j is certainly not in R_u" without a binary search.
+struct __align__(16) UserMeta {
+    uint64_t off_len;  // offset in the low 38 bits, length in the high 26
+    uint64_t bloom;
+    __host__ __device__ int64_t off() const { return (int64_t)(off_len & ((1ull << 38) - 1)); }
+    __host__ __device__ int64_t len() const { return (int64_t)(off_len >> 38); }
+    __host__ __device__ static uint64_t bit(int32_t item) { return 1ull << (((uint32_t)item * 0x9E3779B1u) >> 26); }
+    __host__ __device__ bool maybe_contains(int32_t item) const { return (bloom & bit(item)) != 0; }
+};
+}  // namespace gb
+
 struct gorse_b200_cf {
     gorse_b200_ctx *ctx = nullptr;
     int32_t n_users = 0, n_items = 0, d = 0;
@@ -27,6 +40,8 @@ struct gorse_b200_cf {
     gb::DevBuf<float> P, Q, Q0;
     gb::DevBuf<int64_t> user_off, item_off;
     gb::DevBuf<int32_t> user_items, item_users, active;
+    gb::DevBuf<gb::UserMeta> user_meta;
+    bool all_active = false;  // every user of the shard has feedback: active[k] == u_lo + k
     // ALS scratch
     gb::DevBuf<float> gram;      // d x d
     gb::DevBuf<float> scratch;   // per-row pred/res for long rows + partial grams
@@ -73,6 +88,15 @@ struct SStream {
 };
 
 #ifdef __CUDACC__
+
+__device__ __forceinline__ UserMeta ld_meta(const UserMeta *p)
+{
+    const uint4 r = __ldg(reinterpret_cast<const uint4 *>(p));
+    UserMeta m;
+    m.off_len = (uint64_t)r.x | ((uint64_t)r.y << 32);
+    m.bloom = (uint64_t)r.z | ((uint64_t)r.w << 32);
+    return m;
+}
 
 __device__ __forceinline__ unsigned quad_mask() { return 0xFu << (threadIdx.x & 28u); }
 

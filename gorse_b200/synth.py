@@ -10,13 +10,17 @@ def zipf_weights(n, s=1.0):
     return w / w.sum()
 
 
-def make_feedback(n_users, n_items, n_feedback, seed=0, zipf_s=1.0, n_clusters=0, in_cluster=0.8):
-    """Returns (user_off int64[U+1], user_items int32[|R|]) with |R| <= n_feedback after de-duplication.
+def make_feedback(n_users, n_items, n_feedback, seed=0, zipf_s=1.0, n_clusters=0, in_cluster=0.8, exact=False):
+    """Returns (user_off int64[U+1], user_items int32[|R|]) with |R| <= n_feedback after de-duplication
+    (exact=True over-draws and trims so that |R| == n_feedback whenever enough distinct pairs exist).
 
     Item popularity is Zipf(zipf_s) (uniform when zipf_s == 0).  With n_clusters > 0 a planted block
     structure is added: a user in cluster c draws `in_cluster` of its items from cluster c's items.
     """
     rng = np.random.default_rng(seed)
+    want = n_feedback
+    if exact:
+        n_feedback = int(n_feedback * 1.12) + 16
     extra = max(0, n_feedback - n_users)
     act = rng.lognormal(0.0, 1.0, n_users)
     deg = 1 + rng.multinomial(extra, act / act.sum())
@@ -37,6 +41,16 @@ def make_feedback(n_users, n_items, n_feedback, seed=0, zipf_s=1.0, n_clusters=0
     else:
         items = perm[ranks]
     key = np.unique(users * np.int64(n_items) + items.astype(np.int64))
+    if exact and key.size > want:
+        # trim the surplus at random, never a user's first item (every user keeps >= 1)
+        u_of = key // n_items
+        first = np.ones(key.size, bool)
+        first[1:] = u_of[1:] != u_of[:-1]
+        cand = np.nonzero(~first)[0]
+        drop = rng.choice(cand, size=min(key.size - want, cand.size), replace=False)
+        keep = np.ones(key.size, bool)
+        keep[drop] = False
+        key = key[keep]
     users = (key // n_items).astype(np.int64)
     items = (key % n_items).astype(np.int32)
     off = np.zeros(n_users + 1, np.int64)
