@@ -16,7 +16,27 @@ struct BprView {
     const int32_t *user_items;
     const int32_t *active;      // nullptr when every user of the shard has feedback (active[k] == u_lo + k)
     int32_t n_active, n_items, d, u_lo;
+    // hot items (the head of the popularity distribution) are trained in a striped side table for the duration
+    // of an epoch: piece pc (16 bytes) of hot slot s lives at hot + (pc * hot_pad + s) * GB_HOT_SLOT_FLOATS, i.e.
+    // every piece owns a 128-byte line and the 16 pieces of a row sit in 16 different planes, so the L2 atomic
+    // units of many slices share the load of one hot row (tools/l2_atomic_probe.cu: 2.7x the single-row rate)
+    float *hot;
+    const int32_t *hot_slot;    // per item: slot or -1; nullptr when no item is hot
+    int32_t hot_pad;
 };
+
+#define GB_HOT_SLOT_FLOATS 32
+
+// lane-local reference of item row `it` (base, chunk stride in floats)
+__device__ __forceinline__ float *item_ref(const BprView &v, int32_t it, int32_t slot, int lane4, int &stride)
+{
+    if (slot < 0) {
+        stride = 16;
+        return v.Q + (int64_t)it * v.d + 4 * lane4;
+    }
+    stride = 4 * v.hot_pad * GB_HOT_SLOT_FLOATS;
+    return v.hot + ((int64_t)lane4 * v.hot_pad + slot) * GB_HOT_SLOT_FLOATS;
+}
 
 // factor rows are read and written by every SM concurrently: keep them out of the (non-coherent) L1
 __device__ __forceinline__ float4 ld_row(const float *p) { return __ldcg(reinterpret_cast<const float4 *>(p)); }
@@ -50,25 +70,26 @@ struct Rows {
     float4 p[C], qi[C], qj[C];
 };
 
+// Row references are lane-local: `base` already points at this lane's first float4 and chunk c sits at
+// base + c * stride floats.  A row of the factor tables has stride 16 (cf.cuh quad layout); a hot item row lives
+// in the striped side table (see HotView) where consecutive pieces are whole planes apart.
 template <int C>
-__device__ __forceinline__ void load_rows(Rows<C> &r, const float *Pu, const float *Qi, const float *Qj, int lane4)
+__device__ __forceinline__ void load_rows(Rows<C> &r, const float *Pu, const float *Qi, int si, const float *Qj, int sj)
 {
-    Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
 #pragma unroll
     for (int c = 0; c < C; c++) r.p[c] = ld_row(Pu + 16 * c);
 #pragma unroll
-    for (int c = 0; c < C; c++) r.qi[c] = ld_row(Qi + 16 * c);
+    for (int c = 0; c < C; c++) r.qi[c] = ld_row(Qi + si * c);
 #pragma unroll
-    for (int c = 0; c < C; c++) r.qj[c] = ld_row(Qj + 16 * c);
+    for (int c = 0; c < C; c++) r.qj[c] = ld_row(Qj + sj * c);
 }
 
 // one SGD step by a quad on rows already in registers
 template <int C, bool ATOMIC>
-__device__ __forceinline__ void bpr_step_rows(const Rows<C> &r, float *Pu, float *Qi, float *Qj, int lane4, unsigned mask,
+__device__ __forceinline__ void bpr_step_rows(const Rows<C> &r, float *Pu, float *Qi, int si, float *Qj, int sj, unsigned mask,
                                               float lr, float reg)
 {
     const float4 *p = r.p, *qi = r.qi, *qj = r.qj;
-    Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
     float4 ai = make_float4(0.f, 0.f, 0.f, 0.f), aj = ai;
 #pragma unroll
     for (int c = 0; c < C; c++) {
@@ -82,12 +103,12 @@ __device__ __forceinline__ void bpr_step_rows(const Rows<C> &r, float *Pu, float
         float4 t, o;
         // :477-479  q_i += lr * (g*p - reg*q_i)
         GB_F4_OP(t, __fmaf_rn(f4get(qi[c], k_), nreg, __fmul_rn(g, f4get(p[c], k_))));
-        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qi + 16 * c, o); }
-        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qi[c], k_))); st_row(Qi + 16 * c, o); }
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qi + si * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qi[c], k_))); st_row(Qi + si * c, o); }
         // :481-483  q_j += lr * (-g*p - reg*q_j)
         GB_F4_OP(t, __fmaf_rn(f4get(qj[c], k_), nreg, __fmul_rn(ng, f4get(p[c], k_))));
-        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qj + 16 * c, o); }
-        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qj[c], k_))); st_row(Qj + 16 * c, o); }
+        if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qj + sj * c, o); }
+        else { GB_F4_OP(o, __fmaf_rn(f4get(t, k_), lr, f4get(qj[c], k_))); st_row(Qj + sj * c, o); }
         // :485-488  p_u += lr * (g*(q_i - q_j) - reg*p_u)
         GB_F4_OP(t, __fmaf_rn(f4get(p[c], k_), nreg, __fmul_rn(__fsub_rn(f4get(qi[c], k_), f4get(qj[c], k_)), g)));
         if (ATOMIC) { GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Pu + 16 * c, o); }
@@ -99,8 +120,9 @@ template <int C, bool ATOMIC>
 __device__ __forceinline__ void bpr_step_quad(float *Pu, float *Qi, float *Qj, int lane4, unsigned mask, float lr, float reg)
 {
     Rows<C> r;
-    load_rows<C>(r, Pu, Qi, Qj, lane4);
-    bpr_step_rows<C, ATOMIC>(r, Pu, Qi, Qj, lane4, mask, lr, reg);
+    Pu += 4 * lane4; Qi += 4 * lane4; Qj += 4 * lane4;
+    load_rows<C>(r, Pu, Qi, 16, Qj, 16);
+    bpr_step_rows<C, ATOMIC>(r, Pu, Qi, 16, Qj, 16, mask, lr, reg);
 }
 
 // same step for any d % 16 == 0 without register-resident rows (two passes over L2-hot rows)
@@ -190,18 +212,26 @@ __global__ void __launch_bounds__(256) bpr_epoch_kernel(BprView v, int64_t step0
         // software pipeline: the row gathers of step k are in flight while step k+1 is being sampled
         // (its own chain of 2-3 dependent index loads), so one iteration costs one memory round trip
         constexpr int CC = C > 0 ? C : 1;
-        int32_t u = 0, i = 0, j = -1;
-        if (q < n_steps) sample_triple(v, base, step0 + q, u, i, j);
+        int32_t u = 0, i = 0, j = -1, hi = -1, hj = -1;
+        if (q < n_steps) {
+            sample_triple(v, base, step0 + q, u, i, j);
+            if (v.hot_slot && j >= 0) { hi = __ldg(v.hot_slot + i); hj = __ldg(v.hot_slot + j); }
+        }
         while (q < n_steps) {
             Rows<CC> r;
-            float *Pu = v.P + (int64_t)(u - v.u_lo) * v.d, *Qi = v.Q + (int64_t)i * v.d, *Qj = v.Q + (int64_t)j * v.d;
             const bool live = j >= 0;
-            if (live) load_rows<CC>(r, Pu, Qi, Qj, lane4);
+            int si = 16, sj = 16;
+            float *Pu = v.P + (int64_t)(u - v.u_lo) * v.d + 4 * lane4;
+            float *Qi = item_ref(v, i, hi, lane4, si), *Qj = item_ref(v, live ? j : 0, hj, lane4, sj);
+            if (live) load_rows<CC>(r, Pu, Qi, si, Qj, sj);
             const int64_t qn = q + nq;
-            int32_t un = 0, in = 0, jn = -1;
-            if (qn < n_steps) sample_triple(v, base, step0 + qn, un, in, jn);
-            if (live) bpr_step_rows<CC, ATOMIC>(r, Pu, Qi, Qj, lane4, mask, lr, reg);
-            q = qn; u = un; i = in; j = jn;
+            int32_t un = 0, in = 0, jn = -1, hin = -1, hjn = -1;
+            if (qn < n_steps) {
+                sample_triple(v, base, step0 + qn, un, in, jn);
+                if (v.hot_slot && jn >= 0) { hin = __ldg(v.hot_slot + in); hjn = __ldg(v.hot_slot + jn); }
+            }
+            if (live) bpr_step_rows<CC, ATOMIC>(r, Pu, Qi, si, Qj, sj, mask, lr, reg);
+            q = qn; u = un; i = in; j = jn; hi = hin; hj = hjn;
         }
     } else {
         for (; q < n_steps; q += nq) {
@@ -295,6 +325,26 @@ __global__ void q_apply_scalar_kernel(float *q, float *q0, int64_t n)
     for (; i < n; i += st) { float r = q0[i] + q[i]; q[i] = r; q0[i] = r; }
 }
 
+// hot rows <-> striped side table, one quad-piece per thread
+__global__ void hot_gather_kernel(const float *Q, int d, const int32_t *hot_items, int n_hot, int hot_pad, float *hot)
+{
+    int pieces = d / 4;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_hot * pieces) return;
+    int s = (int)(t / pieces), pc = (int)(t % pieces);
+    float4 v = *reinterpret_cast<const float4 *>(Q + (int64_t)hot_items[s] * d + 4 * pc);
+    *reinterpret_cast<float4 *>(hot + ((int64_t)pc * hot_pad + s) * GB_HOT_SLOT_FLOATS) = v;
+}
+__global__ void hot_scatter_kernel(float *Q, int d, const int32_t *hot_items, int n_hot, int hot_pad, const float *hot)
+{
+    int pieces = d / 4;
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)n_hot * pieces) return;
+    int s = (int)(t / pieces), pc = (int)(t % pieces);
+    float4 v = *reinterpret_cast<const float4 *>(hot + ((int64_t)pc * hot_pad + s) * GB_HOT_SLOT_FLOATS);
+    *reinterpret_cast<float4 *>(Q + (int64_t)hot_items[s] * d + 4 * pc) = v;
+}
+
 static BprView make_view(gorse_b200_cf *cf)
 {
     BprView v;
@@ -302,6 +352,7 @@ static BprView make_view(gorse_b200_cf *cf)
     v.meta = cf->user_meta.p; v.user_items = cf->user_items.p;
     v.active = cf->all_active ? nullptr : cf->active.p;
     v.n_active = cf->n_active; v.n_items = cf->n_items; v.d = cf->d; v.u_lo = cf->u_lo;
+    v.hot = nullptr; v.hot_slot = nullptr; v.hot_pad = 0;  // the striped hot table is switched on by bpr_epoch only
     return v;
 }
 
@@ -476,9 +527,20 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
     if (s1 > s0) {
         if (cf->n_active == 0) { set_error("no user with feedback in this shard"); return GORSE_B200_ERR_STATE; }
         BprView v = make_view(cf);
+        const bool use_hot = cf->n_hot > 0 && cf->d % 16 == 0 && cf->d <= 128;
+        const int hot_threads = cf->n_hot * (cf->d / 4);
+        if (use_hot) {
+            v.hot = cf->hot.p; v.hot_slot = cf->hot_slot.p; v.hot_pad = cf->hot_pad;
+            hot_gather_kernel<<<div_up(hot_threads, 256), 256, 0, c->stream>>>(cf->Q.p, cf->d, cf->hot_items.p, cf->n_hot, cf->hot_pad, cf->hot.p);
+            GB_LAUNCHED(c);
+        }
         if (scatter == GORSE_B200_SCATTER_ATOMIC) launch_epoch<true>(cf, v, s0, s1 - s0, mix64(seed), lr, reg);
         else launch_epoch<false>(cf, v, s0, s1 - s0, mix64(seed), lr, reg);
         GB_LAUNCHED(c);
+        if (use_hot) {
+            hot_scatter_kernel<<<div_up(hot_threads, 256), 256, 0, c->stream>>>(cf->Q.p, cf->d, cf->hot_items.p, cf->n_hot, cf->hot_pad, cf->hot.p);
+            GB_LAUNCHED(c);
+        }
     }
     if (c->world > 1) {
         int64_t n = (int64_t)cf->Q.n;

@@ -1,5 +1,6 @@
 // cf.cu -- CF model state: create/destroy, factor upload/download, normal init, batched Predict.
 #include <algorithm>
+#include <cstdlib>
 #include <thread>
 
 #include "cf.cuh"
@@ -149,6 +150,30 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
         meta[u].bloom = bloom;
     }
 
+    // hot items: an item drawn as the positive of more than ~0.02% of an epoch's triples would serialise on one
+    // L2 atomic unit; P(i) is proportional to sum_{u in R_i} 1/|R_u| (user uniform, then item uniform in the row)
+    std::vector<int32_t> hot_items, hot_slot;
+    {
+        std::vector<double> mass((size_t)n_items, 0.0);
+        for (int32_t u = cf->u_lo; u < cf->u_hi; u++) {
+            int64_t o = user_off[u], len = user_off[u + 1] - o;
+            double w = len ? 1.0 / (double)len : 0.0;
+            for (int64_t t = 0; t < len; t++) mass[(size_t)sorted[(size_t)(o + t)]] += w;
+        }
+        const double total = std::max(1, cf->n_active), thresh = 2e-4 * total;
+        std::vector<int32_t> cand;
+        for (int32_t i = 0; i < n_items; i++) if (mass[i] > thresh) cand.push_back(i);
+        std::sort(cand.begin(), cand.end(), [&](int32_t a, int32_t b) { return mass[a] > mass[b] || (mass[a] == mass[b] && a < b); });
+        if (cand.size() > 1024) cand.resize(1024);
+        if (const char *e = getenv("GORSE_B200_NO_HOT")) { if (*e == '1') cand.clear(); }
+        hot_items = cand;
+        if (!hot_items.empty()) {
+            hot_slot.assign((size_t)n_items, -1);
+            for (size_t s = 0; s < hot_items.size(); s++) hot_slot[(size_t)hot_items[s]] = (int32_t)s;
+        }
+        cf->n_hot = (int32_t)hot_items.size();
+        cf->hot_pad = std::max(64, (cf->n_hot + 63) / 64 * 64);
+    }
     int64_t n_local = cf->u_hi - cf->u_lo;
     if ((st = cf->P.alloc((size_t)n_local * n_factors)) != 0) return fail(st);
     if ((st = cf->Q.alloc((size_t)n_items * n_factors)) != 0) return fail(st);
@@ -157,6 +182,11 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     if ((st = cf->user_items.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
     if ((st = cf->active.alloc(active.size())) != 0) return fail(st);
     if ((st = cf->user_meta.alloc((size_t)n_users)) != 0) return fail(st);
+    if (cf->n_hot) {
+        if ((st = cf->hot_items.alloc(hot_items.size())) != 0) return fail(st);
+        if ((st = cf->hot_slot.alloc(hot_slot.size())) != 0) return fail(st);
+        if ((st = cf->hot.alloc((size_t)(n_factors / 4 + 1) * cf->hot_pad * 32)) != 0) return fail(st);
+    }
     cudaStream_t s = ctx->stream;
     auto up = [&](void *dst, const void *src, size_t bytes) -> int32_t {
         if (bytes == 0) return GORSE_B200_OK;
@@ -167,6 +197,10 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     if ((st = up(cf->user_items.p, sorted.data(), sizeof(int32_t) * (size_t)cf->n_feedback)) != 0) return fail(st);
     if ((st = up(cf->active.p, active.data(), sizeof(int32_t) * active.size())) != 0) return fail(st);
     if ((st = up(cf->user_meta.p, meta.data(), sizeof(UserMeta) * meta.size())) != 0) return fail(st);
+    if (cf->n_hot) {
+        if ((st = up(cf->hot_items.p, hot_items.data(), sizeof(int32_t) * hot_items.size())) != 0) return fail(st);
+        if ((st = up(cf->hot_slot.p, hot_slot.data(), sizeof(int32_t) * hot_slot.size())) != 0) return fail(st);
+    }
     if (has_items) {
         if ((st = cf->item_off.alloc((size_t)n_items + 1)) != 0) return fail(st);
         if ((st = cf->item_users.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
@@ -192,6 +226,7 @@ int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
     cf->P.free(); cf->Q.free(); cf->Q0.free();
     cf->user_off.free(); cf->item_off.free();
     cf->user_items.free(); cf->item_users.free(); cf->active.free(); cf->user_meta.free();
+    cf->hot_items.free(); cf->hot_slot.free(); cf->hot.free();
     cf->gram.free(); cf->scratch.free();
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 3; b++) cf->als_rows[a][b].free();

@@ -42,6 +42,10 @@ struct gorse_b200_cf {
     gb::DevBuf<int32_t> user_items, item_users, active;
     gb::DevBuf<gb::UserMeta> user_meta;
     bool all_active = false;  // every user of the shard has feedback: active[k] == u_lo + k
+    // hot items (BPR): the head of the popularity distribution, trained in a striped side table (bpr.cu HotView)
+    int32_t n_hot = 0, hot_pad = 0;
+    gb::DevBuf<int32_t> hot_items, hot_slot;
+    gb::DevBuf<float> hot;
     // ALS scratch
     gb::DevBuf<float> gram;      // d x d
     gb::DevBuf<float> scratch;   // per-row pred/res for long rows + partial grams

@@ -40,16 +40,21 @@ def make_feedback(n_users, n_items, n_feedback, seed=0, zipf_s=1.0, n_clusters=0
         items = ranks  # keep rank == id so the planted structure is item % n_clusters
     else:
         items = perm[ranks]
-    key = np.unique(users * np.int64(n_items) + items.astype(np.int64))
+    key = users * np.int64(n_items) + items.astype(np.int64)
+    key.sort()  # (np.unique's hash path is ~6x slower at 10^7 keys)
+    if key.size > 1:
+        key = key[np.concatenate(([True], key[1:] != key[:-1]))]
     if exact and key.size > want:
         # trim the surplus at random, never a user's first item (every user keeps >= 1)
         u_of = key // n_items
         first = np.ones(key.size, bool)
         first[1:] = u_of[1:] != u_of[:-1]
         cand = np.nonzero(~first)[0]
-        drop = rng.choice(cand, size=min(key.size - want, cand.size), replace=False)
+        k = min(key.size - want, cand.size)
+        r = rng.random(cand.size)
+        thr = np.partition(r, k - 1)[k - 1]
         keep = np.ones(key.size, bool)
-        keep[drop] = False
+        keep[cand[r <= thr]] = False
         key = key[keep]
     users = (key // n_items).astype(np.int64)
     items = (key % n_items).astype(np.int32)
