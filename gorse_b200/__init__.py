@@ -174,6 +174,24 @@ class CFModel:
     def als_epoch(self, reg, alpha):
         check(lib.gorse_b200_als_epoch(self.h, reg, alpha))
 
+    def fit(self, kind, test_off, test_items, neg_off, neg_items, progress=None, **params):
+        """cf.BPR.Fit / cf.ALS.Fit through gorse_b200_{bpr,als}_fit; params override the reference defaults."""
+        fp = _lib.FitParams()
+        check(lib.gorse_b200_fit_params_default(1 if kind == "als" else 0, C.byref(fp)))
+        fp.n_factors = self.d
+        for k, v in params.items():
+            setattr(fp, k, v)
+        res = _lib.FitResult()
+        test_off = np.ascontiguousarray(test_off, np.int64)
+        test_items = np.ascontiguousarray(test_items, np.int32)
+        neg_off = np.ascontiguousarray(neg_off, np.int64)
+        neg_items = np.ascontiguousarray(neg_items, np.int32)
+        cb = _lib.PROGRESS_FN(lambda user, ep, n, ndcg: int(bool(progress(ep, n, ndcg)))) if progress else None
+        fn = lib.gorse_b200_als_fit if kind == "als" else lib.gorse_b200_bpr_fit
+        check(fn(self.h, C.byref(fp), ptr(test_off), ptr(test_items), ptr(neg_off), ptr(neg_items),
+                 C.cast(cb, C.c_void_p) if cb else None, None, C.byref(res)))
+        return res
+
     def evaluate(self, test_off, test_items, neg_off, neg_items, topk=10):
         test_off = np.ascontiguousarray(test_off, np.int64)
         test_items = np.ascontiguousarray(test_items, np.int32)

@@ -57,6 +57,9 @@ PROTOTYPES = {
     "gorse_b200_bpr_epoch": (C.c_int32, [VP, C.c_float, C.c_float, C.c_int64, C.c_uint64, C.c_int32]),
     "gorse_b200_als_epoch": (C.c_int32, [VP, C.c_float, C.c_float]),
     "gorse_b200_cf_evaluate": (C.c_int32, [VP, VP, VP, VP, VP, C.c_int32, VP]),
+    "gorse_b200_fit_params_default": (C.c_int32, [C.c_int32, VP]),
+    "gorse_b200_bpr_fit": (C.c_int32, [VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "gorse_b200_als_fit": (C.c_int32, [VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "gorse_b200_index_create": (C.c_int32, [VP, C.c_int32, C.c_int32, PVP]),
     "gorse_b200_index_destroy": (C.c_int32, [VP]),
     "gorse_b200_index_add": (C.c_int32, [VP, VP, C.c_int64, C.POINTER(C.c_int64)]),
@@ -65,6 +68,20 @@ PROTOTYPES = {
     "gorse_b200_index_search_indices": (C.c_int32, [VP, VP, C.c_int64, C.c_int32, C.c_int32, VP, VP, VP]),
     "gorse_b200_index_search_range": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int32, C.c_int32, VP, VP, VP]),
 }
+
+
+class FitParams(C.Structure):
+    _fields_ = [("n_factors", C.c_int32), ("n_epochs", C.c_int32), ("lr", C.c_float), ("reg", C.c_float),
+                ("init_mean", C.c_float), ("init_stddev", C.c_float), ("alpha", C.c_float), ("seed", C.c_uint64),
+                ("verbose", C.c_int32), ("candidates", C.c_int32), ("topk", C.c_int32), ("patience", C.c_int32)]
+
+
+class FitResult(C.Structure):
+    _fields_ = [("ndcg", C.c_float), ("precision", C.c_float), ("recall", C.c_float), ("epochs_run", C.c_int32),
+                ("early_stopped", C.c_int32), ("best_epoch", C.c_int32), ("cancelled", C.c_int32)]
+
+
+PROGRESS_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.c_int32, C.c_int32, C.c_float)
 
 
 class GorseB200Error(RuntimeError):

@@ -226,7 +226,7 @@ int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
     cf->P.free(); cf->Q.free(); cf->Q0.free();
     cf->user_off.free(); cf->item_off.free();
     cf->user_items.free(); cf->item_users.free(); cf->active.free(); cf->user_meta.free();
-    cf->hot_items.free(); cf->hot_slot.free(); cf->hot.free();
+    cf->hot_items.free(); cf->hot_slot.free(); cf->hot.free(); cf->hotq.free(); cf->hot_sorted.free(); cf->hot_ctr.free();
     cf->gram.free(); cf->scratch.free();
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 3; b++) cf->als_rows[a][b].free();

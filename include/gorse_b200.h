@@ -157,6 +157,48 @@ int32_t gorse_b200_cf_evaluate(gorse_b200_cf *cf, const int64_t *test_off, const
                                float *out);
 
 /* ------------------------------------------------------------------------------------------
+ * Whole Fit.  Replaces cf.BPR.Fit / cf.ALS.Fit (model/cf/model.go:408-530, 609-775): Init, Evaluate at
+ * epoch 0, the epoch loop, Evaluate every `verbose` epochs and after the last one, early stopping when the
+ * best NDCG is older than `patience` epochs (:508-517).  The shim may call this once per Fit, or keep the
+ * loop in Go and call the per-epoch entry points.  Hyper-parameters are model.Params
+ * (model/params.go) + cf.FitConfig (model/cf/model.go:50-65); FitConfig.Jobs has no equivalent.
+ * The factor tables of `cf` are created with n_factors = params->n_factors by the caller.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_factors;   /* NFactors, default 16 */
+    int32_t n_epochs;    /* NEpochs, default 100 (BPR) / 50 (ALS) */
+    float lr;            /* Lr, BPR only, default 0.05 */
+    float reg;           /* Reg, default 0.01 (BPR) / 0.06 (ALS) */
+    float init_mean;     /* InitMean, default 0 */
+    float init_stddev;   /* InitStdDev, default 0.001 (BPR) / 0.1 (ALS) */
+    float alpha;         /* Alpha (eALS weight), ALS only, default 0.001 */
+    uint64_t seed;       /* RandomState */
+    int32_t verbose;     /* FitConfig.Verbose, default 10 */
+    int32_t candidates;  /* FitConfig.Candidates, default 100 (the caller samples the negatives) */
+    int32_t topk;        /* FitConfig.TopK, default 10 */
+    int32_t patience;    /* FitConfig.Patience, default 0 = no early stopping */
+} gorse_b200_fit_params;
+
+typedef struct {
+    float ndcg, precision, recall; /* cf.Score of the LAST evaluation; all zero when cancelled (:491-493) */
+    int32_t epochs_run;
+    int32_t early_stopped, best_epoch;
+    int32_t cancelled;
+} gorse_b200_fit_result;
+
+/* called after every epoch (monitor span.Add(1), model.go:519); ndcg < 0 when the epoch was not evaluated.
+ * Return non-zero to cancel (ctx.Err() != nil): Fit then returns a zero Score like the reference. */
+typedef int32_t (*gorse_b200_progress_fn)(void *user, int32_t epoch, int32_t n_epochs, float ndcg);
+
+int32_t gorse_b200_fit_params_default(int32_t als, gorse_b200_fit_params *params);
+int32_t gorse_b200_bpr_fit(gorse_b200_cf *cf, const gorse_b200_fit_params *params, const int64_t *test_off,
+                           const int32_t *test_items, const int64_t *neg_off, const int32_t *neg_items,
+                           gorse_b200_progress_fn progress, void *user, gorse_b200_fit_result *result);
+int32_t gorse_b200_als_fit(gorse_b200_cf *cf, const gorse_b200_fit_params *params, const int64_t *test_off,
+                           const int32_t *test_items, const int64_t *neg_off, const int32_t *neg_items,
+                           gorse_b200_progress_fn progress, void *user, gorse_b200_fit_result *result);
+
+/* ------------------------------------------------------------------------------------------
  * Brute-force index.  Replaces ann.Bruteforce[[]float32] (common/ann/bruteforce.go:24-83)
  * behind ann.Index (common/ann/ann.go:21-25).
  * ---------------------------------------------------------------------------------------- */
