@@ -235,6 +235,21 @@ class BruteforceIndex:
         check(lib.gorse_b200_index_len(self.h, C.byref(n)))
         return n.value
 
+    # test hooks (not part of the public header)
+    def debug_fallback_rows(self):
+        n = C.c_int64(0)
+        raw = C.CDLL(_lib.LIB_PATH)
+        raw.gorse_b200_debug_topk_fallback_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        check(raw.gorse_b200_debug_topk_fallback_rows(self.h, C.byref(n)))
+        return n.value
+
+    def debug_stage1_scores(self, q0, q1):
+        out = np.zeros((q1 - q0, len(self)), np.float32)
+        raw = C.CDLL(_lib.LIB_PATH)
+        raw.gorse_b200_debug_topk_scores.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
+        check(raw.gorse_b200_debug_topk_scores(self.h, q0, q1, ptr(out)))
+        return out
+
     def _out(self, nq, k):
         return (np.full((nq, max(k, 1)), -1, np.int32), np.zeros((nq, max(k, 1)), np.float32), np.zeros(nq, np.int32))
 

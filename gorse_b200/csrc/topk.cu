@@ -94,8 +94,8 @@ __device__ __forceinline__ void list_insert(float *ld, int32_t *li, int &len, in
 //   cand:      optional candidate lists [nq][cand_stride] (idx < 0 = empty slot) -> stage-2 re-rank
 __global__ void __launch_bounds__(128)
 topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_ptr, const int64_t *q_idx, int64_t q0,
-                  int64_t nq, int k, const int32_t *cand, const int32_t *cand_count, int cand_stride, int32_t *out_idx,
-                  float *out_dist, int32_t *out_count, int prune0, int *nan_flag)
+                  int64_t nq, int k, const int32_t *cand, const int32_t *cand_count, int cand_stride, const int32_t *row_list,
+                  int32_t *out_idx, float *out_dist, int32_t *out_count, int prune0, int *nan_flag)
 {
     extern __shared__ unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -104,7 +104,8 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
     float *qs = reinterpret_cast<float *>(sm_raw) + (size_t)2 * nw * k + (size_t)wid * d;
     const int lane4 = lane & 3, quad = lane >> 2;
     const unsigned qmask = quad_mask();
-    for (int64_t qi = (int64_t)blockIdx.x * nw + wid; qi < nq; qi += (int64_t)gridDim.x * nw) {
+    for (int64_t slot = (int64_t)blockIdx.x * nw + wid; slot < nq; slot += (int64_t)gridDim.x * nw) {
+        const int64_t qi = row_list ? (int64_t)row_list[slot] : slot;
         int64_t self = -1;
         const float *qsrc;
         if (q_ptr) qsrc = q_ptr + qi * d;
@@ -178,8 +179,8 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
 }
 
 int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k,
-                     const int32_t *d_cand, const int32_t *d_cand_count, int cand_stride, int32_t *d_idx, float *d_dist,
-                     int32_t *d_count, int prune0, int *d_nan)
+                     const int32_t *d_cand, const int32_t *d_cand_count, int cand_stride, const int32_t *row_list,
+                     int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan)
 {
     gorse_b200_ctx *c = ix->ctx;
     const int warps = 4;
@@ -188,7 +189,7 @@ int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qi
     GB_CUDA(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nq + warps - 1) / warps, (int64_t)c->sm_count * 8));
     topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, nq, k, d_cand,
-                                                         d_cand_count, cand_stride, d_idx, d_dist, d_count, prune0, d_nan);
+                                                         d_cand_count, cand_stride, row_list, d_idx, d_dist, d_count, prune0, d_nan);
     GB_LAUNCHED(c);
     return GORSE_B200_OK;
 }
@@ -233,7 +234,7 @@ static int32_t search_common(gorse_b200_index *ix, const float *h_queries, const
     if (mma_path_eligible(ix, nq, k)) {
         st = search_mma(ix, d_q.p, d_qidx.p, q0, nq, k, prune0, d_idx.p, d_dist.p, d_count.p, d_nan.p);
     } else {
-        st = launch_exact(ix, d_q.p, d_qidx.p, q0, nq, k, nullptr, nullptr, 0, d_idx.p, d_dist.p, d_count.p, prune0, d_nan.p);
+        st = launch_exact(ix, d_q.p, d_qidx.p, q0, nq, k, nullptr, nullptr, 0, nullptr, d_idx.p, d_dist.p, d_count.p, prune0, d_nan.p);
     }
     if (st) return done(st);
     int h_nan = 0;
@@ -278,6 +279,7 @@ int32_t gorse_b200_index_destroy(gorse_b200_index *ix)
     ix->X.free();
     ix->Xb.free();
     ix->norm.free();
+    ix->perm.free();
     delete ix;
     return GORSE_B200_OK;
 }
@@ -351,6 +353,46 @@ int32_t gorse_b200_index_search_range(gorse_b200_index *ix, int64_t q0, int64_t 
         return GORSE_B200_ERR_RANGE;
     }
     return search_common(ix, nullptr, nullptr, q0, q1 - q0, k, prune0, idx_out, dist_out, count_out);
+}
+
+// ---- test hooks (not part of include/gorse_b200.h) -------------------------------------------------------
+// rows of the searches since the last call that fell back to the exact scan
+int32_t gorse_b200_debug_topk_fallback_rows(gorse_b200_index *ix, int64_t *rows)
+{
+    GB_CHECK_ARG(ix != nullptr && rows != nullptr, "NULL argument");
+    *rows = ix->last_fallback_rows;
+    ix->last_fallback_rows = 0;
+    return GORSE_B200_OK;
+}
+
+// dense stage-1 (tensor core) scores of stored vectors [q0, q1) against all vectors, in ORIGINAL column order:
+// out[(q - q0) * n + x].  Small problems only.
+int32_t gorse_b200_debug_topk_scores(gorse_b200_index *ix, int64_t q0, int64_t q1, float *out)
+{
+    GB_CHECK_ARG(ix != nullptr && out != nullptr, "NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    GB_CHECK_ARG(q0 >= 0 && q1 > q0 && q1 <= ix->n, "bad range");
+    ScopedDevice sd(ix->ctx->device);
+    gorse_b200_ctx *c = ix->ctx;
+    const int64_t nq = q1 - q0, n_cols = (ix->n + 127) / 128 * 128;
+    DevBuf<float> dense, d_dist;
+    DevBuf<int32_t> d_idx, d_count;
+    DevBuf<int> d_nan;
+    int32_t st;
+    auto done = [&](int32_t s) { cudaStreamSynchronize(c->stream); dense.free(); d_dist.free(); d_idx.free(); d_count.free(); d_nan.free(); ix->dbg_scores = nullptr; return s; };
+    if ((st = dense.alloc((size_t)nq * n_cols)) || (st = d_idx.alloc(nq)) || (st = d_dist.alloc(nq)) || (st = d_count.alloc(nq)) || (st = d_nan.alloc(1))) return done(st);
+    cudaMemsetAsync(d_nan.p, 0, sizeof(int), c->stream);
+    ix->dbg_scores = dense.p;
+    if ((st = search_mma(ix, nullptr, nullptr, q0, nq, 1, 0, d_idx.p, d_dist.p, d_count.p, d_nan.p))) return done(st);
+    std::vector<float> h((size_t)nq * n_cols);
+    std::vector<int32_t> perm((size_t)ix->n);
+    cudaError_t e = cudaMemcpyAsync(h.data(), dense.p, sizeof(float) * h.size(), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(perm.data(), ix->perm.p, sizeof(int32_t) * perm.size(), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("debug scores: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    for (int64_t r = 0; r < nq; r++)
+        for (int64_t p = 0; p < ix->n; p++) out[r * ix->n + perm[p]] = h[r * n_cols + p];
+    return done(GORSE_B200_OK);
 }
 
 }  // extern "C"

@@ -10,16 +10,21 @@ struct gorse_b200_index {
     int64_t n = 0, cap = 0;
     gb::DevBuf<float> X;            // [cap x d] fp32, row-major: the vectors as added (exact re-rank reads these)
     gb::DevBuf<__nv_bfloat16> Xb;   // [n_pad x d] bf16 mirror feeding the tensor cores (built lazily)
-    gb::DevBuf<float> norm;         // per-vector fp32 norms / error-bound terms (built lazily)
+    gb::DevBuf<float> norm;         // per-vector fp32 norms (+ max at [n]), built lazily
+    gb::DevBuf<int32_t> perm;       // mirror row p holds vector perm[p] (random: the first columns are a uniform sample)
+    float max_norm = 0.f;
     bool mma_ready = false;
+    float *dbg_scores = nullptr;    // tests only: dense stage-1 scores
+    int64_t last_fallback_rows = 0; // rows of the last searches that needed the exact scan
     std::mutex mu;
 };
 
 namespace gb {
 
+// exact scan / re-rank.  row_list != nullptr: only those query rows (nq = length of the list) are processed
 int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k,
-                     const int32_t *d_cand, const int32_t *d_cand_count, int cand_stride, int32_t *d_idx, float *d_dist,
-                     int32_t *d_count, int prune0, int *d_nan);
+                     const int32_t *d_cand, const int32_t *d_cand_count, int cand_stride, const int32_t *row_list,
+                     int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan);
 
 bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k);
 int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,

@@ -1,14 +1,595 @@
-// topk_mma.cu -- stage 1 of the brute-force search on the tensor cores (tcgen05 + TMA), see topk.cu.
+// topk_mma.cu -- stage 1 of the brute-force search on the 5th-generation tensor cores.
+//
+//   scores[q][x] = <bf16(q'), bf16(x')>   (q', x' = vectors, for Euclidean augmented so that the score is
+//                                          q.x - |x|^2/2, i.e. larger = closer for both metrics)
+// computed by tcgen05.mma (cta_group::1, kind::f16, M=128, N=128, K=16 per instruction, fp32 accumulators in TMEM),
+// operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) through an mbarrier ring.  The N x N score matrix
+// is never written: the epilogue warps read each accumulator tile out of TMEM (tcgen05.ld 32x32b: one thread = one
+// query row) and keep only columns whose score clears a per-row threshold, appending (column, score) to a small
+// per-row candidate list.  Stage 2 (topk.cu) re-ranks the candidates exactly in the reference's fp32 order.
+//
+// Threshold without a second pass: the vectors are stored in a random column permutation, so the first m columns are a
+// uniform sample.  For those the epilogue tracks each row's 8 best scores; theta = 8th best - 2*eps is then fixed,
+// the sweep continues over all columns (the first m are revisited at the end) and pushes score >= theta.
+//   * soundness: every true top-k element has score >= (k-th best approximate score) - 2*eps  (|score - exact| <= eps,
+//     eps from bf16 rounding: 1.02 * 2^-8 * |q| * max|x| + ...).  Stage 2 verifies that at least k candidates clear
+//     theta + 2*eps, which makes the candidate set a superset of the true top-k; rows that fail the check (or overflow
+//     their list) are redone by the exact scan.  With m = N/64 and the 8th best, a row fails with probability ~2e-4.
+//
+// Roofline class: tensor pipe.  F = 2 * nq * N * Kp flop per sweep.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <random>
+
+#include "cf.cuh"
 #include "topk.cuh"
 
 namespace gb {
+namespace mma {
 
-bool mma_path_eligible(const gorse_b200_index *, int64_t, int) { return false; }
+constexpr int BM = 128, BN = 128, BK = 64;     // tile rows (queries), tile columns (vectors), k-block (bf16 elements)
+constexpr int TILES_M = 2;                     // query tiles per CTA (both multiply every B tile)
+constexpr int MAX_KB = 3;                      // k-blocks per tile: Kp <= 192
+constexpr int CAP = 1024;                      // candidate slots per query row
+constexpr int R_TOP = 8;                       // sample order statistic that fixes the threshold
+constexpr int THREADS = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr uint32_t TILE_BYTES = BM * BK * 2;   // one [128 x 64] bf16 k-block tile = 16 KB
 
-int32_t search_mma(gorse_b200_index *, const float *, const int64_t *, int64_t, int64_t, int, int, int32_t *, float *, int32_t *, int *)
+__device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
-    set_error("tensor-core search path not built");
-    return GORSE_B200_ERR_UNSUPPORTED;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s32(bar)), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s32(dst)),
+                 "l"(map), "r"(s32(bar)), "r"(x), "r"(y)
+                 : "memory");
+}
+// K-major, 128-byte swizzle: LBO = 1 (ignored), SBO = 8 rows * 128 B = 1024 B, descriptor version 1, layout type 2
+__device__ __forceinline__ uint64_t umma_desc(const void *smem_tile, uint32_t k_byte_off)
+{
+    const uint32_t addr = s32(smem_tile) + k_byte_off;
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Params {
+    int64_t n;            // real vectors
+    int32_t n_tiles;      // ceil(n / 128)
+    int32_t m_tiles;      // sample tiles (the sweep revisits them at the end)
+    int32_t kb;           // k-blocks (Kp / 64)
+    int64_t nq;           // real query rows of this launch
+    int32_t n_groups;     // ceil(nq / 256)
+    const float *eps;     // [nq] error margin per query row
+    int32_t *cand_col;    // [nq][CAP] permuted column index
+    float *cand_val;      // [nq][CAP]
+    int32_t *cand_cnt;    // [nq] pushes (may exceed CAP)
+    float *theta;         // [nq] threshold used
+    float *dbg;           // optional dense [nq][n_tiles*128] score dump (tests)
+};
+
+// instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+template <int STAGES>
+__global__ void __launch_bounds__(THREADS, 1)
+topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params P)
+{
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem_a = smem;                                              // [TILES_M][kb] tiles
+    uint8_t *smem_b = smem_a + (size_t)TILES_M * P.kb * TILE_BYTES;      // [STAGES][kb] tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + (size_t)STAGES * P.kb * TILE_BYTES);
+    uint64_t *full = bars, *empty = bars + STAGES, *a_full = bars + 2 * STAGES, *a_empty = a_full + 1;
+    uint64_t *t_full = a_empty + 1, *t_empty = t_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int total_tiles = P.n_tiles + P.m_tiles;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0, ag = 0;
+            for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
+                mbar_wait(a_empty, (ag & 1) ^ 1);  // MMA of the previous group no longer reads A
+                mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
+                for (int m = 0; m < TILES_M; m++)
+                    for (int kb = 0; kb < P.kb; kb++)
+                        tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
+                for (int t = 0; t < total_tiles; t++, it++) {
+                    const int s = it % STAGES;
+                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&full[s], (uint32_t)P.kb * TILE_BYTES);
+                    const int bt = t < P.n_tiles ? t : t - P.n_tiles;
+                    for (int kb = 0; kb < P.kb; kb++)
+                        tma_load_2d(smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES, &map_b, kb * BK, bt * BN, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            uint32_t it = 0, ag = 0, at = 0;
+            for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
+                mbar_wait(a_full, ag & 1);
+                for (int t = 0; t < total_tiles; t++, it++, at++) {
+                    const int s = it % STAGES, as = at & 1;
+                    mbar_wait(&t_empty[as], ((at >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
+                    mbar_wait(&full[s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    for (int m = 0; m < TILES_M; m++) {
+                        const uint32_t d = tmem_base + (uint32_t)((m * 2 + as) * BN);
+                        for (int kb = 0; kb < P.kb; kb++) {
+                            const uint8_t *ta = smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES;
+                            const uint8_t *tb = smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES;
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++)
+                                umma_bf16(d, umma_desc(ta, k * 32), umma_desc(tb, k * 32), IDESC, (kb | k) != 0);
+                        }
+                    }
+                    umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
+                    umma_commit(&t_full[as]);    // both accumulators of this stage are complete
+                }
+                umma_commit(a_empty);
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: 8 warps = 2 query tiles x 128 rows, one thread per row =====
+        const int ew = warp - 4, m = ew >> 2;
+        const uint32_t lane_base = (uint32_t)((ew & 3) * 32) << 16;  // a warp may only touch its own 32 TMEM lanes
+        uint32_t at = 0;
+        for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
+            const int64_t row = (int64_t)(g * TILES_M + m) * BM + (ew & 3) * 32 + lane;
+            const bool row_ok = row < P.nq;
+            const float eps = row_ok ? P.eps[row] : 0.f;
+            float top[R_TOP];
+#pragma unroll
+            for (int r = 0; r < R_TOP; r++) top[r] = -INFINITY;
+            float theta = -INFINITY;
+            int cnt = 0;
+            int32_t *ccol = P.cand_col + (row_ok ? row : 0) * CAP;
+            float *cval = P.cand_val + (row_ok ? row : 0) * CAP;
+            for (int t = 0; t < total_tiles; t++, at++) {
+                const int as = at & 1;
+                const bool sample = t < P.m_tiles;
+                if (t == P.m_tiles) theta = top[R_TOP - 1] - 2.f * eps;
+                const int bt = t < P.n_tiles ? t : t - P.n_tiles;
+                mbar_wait(&t_full[as], (at >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t acc = tmem_base + lane_base + (uint32_t)((m * 2 + as) * BN);
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t v[32];
+                    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the data-dependent pushes
+                    tmem_ld32(acc + c0, v);
+                    const int64_t col0 = (int64_t)bt * BN + c0;
+                    if (P.dbg && row_ok && t < P.n_tiles) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) P.dbg[row * ((int64_t)P.n_tiles * BN) + col0 + e] = __uint_as_float(v[e]);
+                    }
+                    if (sample) {
+#pragma unroll
+                        for (int e = 0; e < 32; e++) {
+                            const float x = __uint_as_float(v[e]);
+                            if (x > top[R_TOP - 1] && col0 + e < P.n) {
+                                // insertion into the sorted 8 best (rare after the first few hundred columns)
+                                float cur = x;
+#pragma unroll
+                                for (int r = 0; r < R_TOP; r++) {
+                                    const float hi = fmaxf(top[r], cur);
+                                    cur = fminf(top[r], cur);
+                                    top[r] = hi;
+                                }
+                            }
+                        }
+                    } else {
+                        // one compare per 4 columns in the common case
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const float mx = fmaxf(fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])),
+                                                   fmaxf(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
+                            if (mx >= theta) {
+#pragma unroll
+                                for (int f = 0; f < 4; f++) {
+                                    const float x = __uint_as_float(v[e + f]);
+                                    if (x >= theta && col0 + e + f < P.n && row_ok) {
+                                        if (cnt < CAP) { ccol[cnt] = (int32_t)(col0 + e + f); cval[cnt] = x; }
+                                        cnt++;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&t_empty[as]);
+            }
+            if (row_ok) { P.cand_cnt[row] = cnt; P.theta[row] = theta; }
+        }
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ---- mirror construction ----------------------------------------------------------------------------
+// row p of the mirror = bf16 of vector perm[p] (zero rows beyond n); Euclidean appends hi/lo of -|x|^2/2
+__global__ void build_mirror_kernel(const float *X, int64_t n, int d, const int32_t *perm, int64_t n_pad, int kp, int metric,
+                                    __nv_bfloat16 *Xb, float *norm /* [n] |x| by original index */)
+{
+    const int64_t p = blockIdx.x;
+    __nv_bfloat16 *dst = Xb + p * kp;
+    if (p >= n) {
+        for (int k = threadIdx.x; k < kp; k += blockDim.x) dst[k] = __float2bfloat16(0.f);
+        return;
+    }
+    const int64_t src = perm[p];
+    const float *x = X + src * d;
+    __shared__ float s_sum[32];
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) { float v = x[k]; ss = __fmaf_rn(v, v, ss); dst[k] = __float2bfloat16(v); }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_sum[w];
+        norm[src] = sqrtf(tot);
+        int k = d;
+        if (metric == GORSE_B200_METRIC_EUCLIDEAN) {
+            const float a = -0.5f * tot;
+            const __nv_bfloat16 hi = __float2bfloat16(a);
+            const __nv_bfloat16 lo = __float2bfloat16(a - __bfloat162float(hi));
+            dst[k++] = hi;
+            dst[k++] = lo;
+        }
+        for (; k < kp; k++) dst[k] = __float2bfloat16(0.f);
+    }
+    // (columns d.. are written by thread 0 only; columns < d by the loop above)
+}
+
+// query mirror rows + per-row eps; queries come from q_ptr, or from X rows (q_idx / q0 + i)
+__global__ void build_queries_kernel(const float *X, const float *q_ptr, const int64_t *q_idx, int64_t q0, int64_t nq, int64_t nq_pad,
+                                     int d, int kp, int metric, float max_norm, __nv_bfloat16 *Qb, float *eps)
+{
+    const int64_t r = blockIdx.x;
+    __nv_bfloat16 *dst = Qb + r * kp;
+    if (r >= nq) {
+        for (int k = threadIdx.x; k < kp; k += blockDim.x) dst[k] = __float2bfloat16(0.f);
+        return;
+    }
+    const float *q = q_ptr ? q_ptr + r * d : X + (q_idx ? q_idx[r] : q0 + r) * d;
+    __shared__ float s_sum[32];
+    float ss = 0.f;
+    for (int k = threadIdx.x; k < d; k += blockDim.x) { float v = q[k]; ss = __fmaf_rn(v, v, ss); dst[k] = __float2bfloat16(v); }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) tot += s_sum[w];
+        const float qn = sqrtf(tot);
+        int k = d;
+        if (metric == GORSE_B200_METRIC_EUCLIDEAN) { dst[k++] = __float2bfloat16(1.f); dst[k++] = __float2bfloat16(1.f); }
+        for (; k < kp; k++) dst[k] = __float2bfloat16(0.f);
+        // |approx - exact| <= eps: bf16 rounding of both operands (2^-8 relative on each product, Cauchy-Schwarz), fp32
+        // accumulation in the tensor core and in the reference, and for Euclidean the hi/lo split of |x|^2/2 plus the
+        // rounding of the reference's own distance.  NaN/Inf inputs make eps NaN -> every compare fails -> exact fallback.
+        float e = 1.02f * 0.00390625f * qn * max_norm;
+        if (metric == GORSE_B200_METRIC_EUCLIDEAN) e += 6.2e-5f * (tot + max_norm * max_norm);
+        eps[r] = e;
+    }
+}
+
+__global__ void max_kernel(const float *v, int64_t n, float *out)
+{
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, v[i] == v[i] ? v[i] : INFINITY);
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));  // non-negative floats order as ints
+}
+
+// ---- stage 2a: prune each row's candidates to the rigorous window and translate to original ids -------------
+// one warp per row; bitonic sort of <= CAP (value, column) pairs by value descending in shared memory
+__global__ void __launch_bounds__(128)
+prune_kernel(const int32_t *cand_col, const float *cand_val, const int32_t *cand_cnt, const float *theta, const float *eps,
+             const int32_t *perm, const int64_t *q_idx, int64_t q0, bool self_skip, int64_t nq, int k, int32_t *out_ids /* [nq][CAP] */,
+             int32_t *out_cnt, int32_t *fallback_flag)
+{
+    extern __shared__ uint8_t sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float *sv = reinterpret_cast<float *>(sm) + (size_t)warp * mma::CAP;
+    int32_t *sc = reinterpret_cast<int32_t *>(reinterpret_cast<float *>(sm) + (size_t)nw * mma::CAP) + (size_t)warp * mma::CAP;
+    for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < nq; row += (int64_t)gridDim.x * nw) {
+        const int raw = cand_cnt[row];
+        int32_t *oi = out_ids + row * mma::CAP;
+        const int64_t self = self_skip ? (q_idx ? q_idx[row] : q0 + row) : -1;
+        bool bad = raw > mma::CAP || !(eps[row] == eps[row]) || !(theta[row] == theta[row]);
+        const int n = min(raw, mma::CAP);
+        int np2 = 32;
+        while (np2 < n) np2 <<= 1;
+        for (int e = lane; e < np2; e += 32) {
+            float v = -INFINITY;
+            int32_t c = -1;
+            if (e < n) {
+                c = perm[cand_col[row * mma::CAP + e]];  // original id
+                v = cand_val[row * mma::CAP + e];
+                if (c == self) v = -INFINITY;            // SearchIndex never returns the query itself
+            }
+            sv[e] = v;
+            sc[e] = c;
+        }
+        __syncwarp();
+        for (int size = 2; size <= np2; size <<= 1)
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int e = lane; e < np2 / 2; e += 32) {
+                    const int lo = 2 * e - (e & (stride - 1)), hi = lo + stride;
+                    const bool desc = (lo & size) == 0;
+                    const float a = sv[lo], b = sv[hi];
+                    if (desc ? a < b : a > b) { sv[lo] = b; sv[hi] = a; const int32_t t = sc[lo]; sc[lo] = sc[hi]; sc[hi] = t; }
+                }
+                __syncwarp();
+            }
+        // validity: at least k candidates clear theta + 2 eps, i.e. the k-th best approximate score is known exactly
+        const float two_eps = 2.f * eps[row];
+        int w = 0;
+        if (!bad) {
+            const int have = n - (self >= 0 ? 1 : 0);  // upper bound; -inf entries sort last anyway
+            if (have < k || !(sv[k - 1] >= theta[row] + two_eps)) bad = true;
+        }
+        if (!bad) {
+            const float lim = sv[k - 1] - two_eps;
+            // window = prefix of the sorted list with value >= lim
+            int cntw = 0;
+            for (int e0 = 0; e0 < np2; e0 += 32) {
+                const int e = e0 + lane;
+                const bool in = e < n && sv[e] >= lim && sc[e] >= 0 && sv[e] > -INFINITY;
+                const unsigned mk = __ballot_sync(0xffffffffu, in);
+                if (in) oi[cntw + __popc(mk & ((1u << lane) - 1))] = sc[e];
+                cntw += __popc(mk);
+                if (mk != 0xffffffffu) break;
+            }
+            w = cntw;
+        }
+        if (lane == 0) {
+            out_cnt[row] = bad ? 0 : w;
+            if (bad) fallback_flag[row] = 1;
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void compact_flags_kernel(const int32_t *flag, int64_t nq, int32_t *list, int32_t *n_list)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < nq && flag[r]) list[atomicAdd(n_list, 1)] = (int32_t)r;
+}
+
+}  // namespace mma
+
+// ---- host side --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int32_t make_map(CUtensorMap *map, const void *base, int64_t rows, int kp)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return GORSE_B200_ERR_CUDA; }
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)mma::BK, (cuuint32_t)mma::BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with %d", (int)r); return GORSE_B200_ERR_CUDA; }
+    return GORSE_B200_OK;
+}
+
+static int kp_of(const gorse_b200_index *ix)
+{
+    int d = ix->d + (ix->metric == GORSE_B200_METRIC_EUCLIDEAN ? 2 : 0);
+    return (d + mma::BK - 1) / mma::BK * mma::BK;
+}
+
+bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k)
+{
+    if (const char *e = getenv("GORSE_B200_TOPK_EXACT")) if (*e == '1') return false;
+    const int kp = kp_of(ix);
+    // the sample needs >= 32 tiles to make theta tight; small problems are faster on the exact scan anyway
+    return kp <= mma::BK * mma::MAX_KB && k >= 1 && k <= 128 && ix->n >= 32768 && nq >= 64 && ix->n < (1ll << 31);
+}
+
+static int32_t ensure_mirror(gorse_b200_index *ix)
+{
+    if (ix->mma_ready) return GORSE_B200_OK;
+    gorse_b200_ctx *c = ix->ctx;
+    const int kp = kp_of(ix);
+    const int64_t n_pad = (ix->n + mma::BN - 1) / mma::BN * mma::BN;
+    GB_TRY(ix->Xb.alloc((size_t)n_pad * kp));
+    GB_TRY(ix->norm.alloc((size_t)ix->n + 1));
+    GB_TRY(ix->perm.alloc((size_t)ix->n));
+    std::vector<int32_t> perm((size_t)ix->n);
+    for (int64_t i = 0; i < ix->n; i++) perm[i] = (int32_t)i;
+    std::mt19937_64 rng(0x9E3779B97F4A7C15ull ^ (uint64_t)ix->n);
+    std::shuffle(perm.begin(), perm.end(), rng);
+    GB_CUDA(cudaMemcpyAsync(ix->perm.p, perm.data(), sizeof(int32_t) * perm.size(), cudaMemcpyHostToDevice, c->stream));
+    mma::build_mirror_kernel<<<(unsigned)n_pad, 128, 0, c->stream>>>(ix->X.p, ix->n, ix->d, ix->perm.p, n_pad, kp, ix->metric, ix->Xb.p, ix->norm.p);
+    GB_LAUNCHED(c);
+    GB_CUDA(cudaMemsetAsync(ix->norm.p + ix->n, 0, sizeof(float), c->stream));
+    mma::max_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(ix->norm.p, ix->n, ix->norm.p + ix->n);
+    GB_LAUNCHED(c);
+    GB_CUDA(cudaMemcpyAsync(&ix->max_norm, ix->norm.p + ix->n, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    GB_CUDA(cudaStreamSynchronize(c->stream));  // perm (host) dies here
+    ix->mma_ready = true;
+    return GORSE_B200_OK;
+}
+
+int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,
+                   int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan)
+{
+    gorse_b200_ctx *c = ix->ctx;
+    GB_TRY(ensure_mirror(ix));
+    const int kp = kp_of(ix), kb = kp / mma::BK;
+    const int64_t n_pad = (ix->n + mma::BN - 1) / mma::BN * mma::BN;
+    const int n_tiles = (int)(n_pad / mma::BN);
+    int m_tiles = std::max(32, (int)((ix->n / 64 + mma::BN - 1) / mma::BN));
+    m_tiles = std::min(m_tiles, n_tiles);
+    const bool self_skip = d_q == nullptr;
+    // stages from the shared-memory budget
+    const size_t a_bytes = (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;
+    int stages = (int)std::min<size_t>(4, (200 * 1024 - a_bytes) / b_stage);
+    if (stages < 2) { set_error("search_mma: Kp = %d does not fit", kp); return GORSE_B200_ERR_UNSUPPORTED; }
+    const size_t smem = a_bytes + (size_t)stages * b_stage + 1024 /*align*/ + 256 /*barriers*/;
+
+    CUtensorMap map_b;
+    GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
+    // queries are processed in chunks so that the candidate lists stay modest
+    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM * 4;
+    DevBuf<__nv_bfloat16> Qb;
+    DevBuf<float> eps, cval, theta;
+    DevBuf<int32_t> ccol, ccnt, ids, idcnt, flag, flist;
+    int32_t st = GORSE_B200_OK;
+    auto done = [&](int32_t s) {
+        cudaStreamSynchronize(c->stream);
+        Qb.free(); eps.free(); cval.free(); theta.free(); ccol.free(); ccnt.free(); ids.free(); idcnt.free(); flag.free(); flist.free();
+        return s;
+    };
+    const int64_t cq = std::min(nq, chunk), cq_pad = (cq + 255) / 256 * 256;
+    if ((st = Qb.alloc((size_t)cq_pad * kp)) || (st = eps.alloc(cq)) || (st = cval.alloc((size_t)cq * mma::CAP)) || (st = theta.alloc(cq)) ||
+        (st = ccol.alloc((size_t)cq * mma::CAP)) || (st = ccnt.alloc(cq)) || (st = ids.alloc((size_t)cq * mma::CAP)) || (st = idcnt.alloc(cq)) ||
+        (st = flag.alloc(cq)) || (st = flist.alloc(cq + 1)))
+        return done(st);
+    auto kern = stages >= 4 ? mma::topk_mma_kernel<4> : stages == 3 ? mma::topk_mma_kernel<3> : mma::topk_mma_kernel<2>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("search_mma smem attr: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    for (int64_t off = 0; off < nq; off += cq) {
+        const int64_t n_this = std::min(cq, nq - off), n_this_pad = (n_this + 255) / 256 * 256;
+        const float *qp = d_q ? d_q + off * ix->d : nullptr;
+        const int64_t *qi = d_qidx ? d_qidx + off : nullptr;
+        mma::build_queries_kernel<<<(unsigned)n_this_pad, 128, 0, c->stream>>>(ix->X.p, qp, qi, q0 + off, n_this, n_this_pad, ix->d, kp, ix->metric,
+                                                                              ix->max_norm, Qb.p, eps.p);
+        c->launches++;
+        CUtensorMap map_a;
+        if ((st = make_map(&map_a, Qb.p, n_this_pad, kp))) return done(st);
+        mma::Params P;
+        P.n = ix->n; P.n_tiles = n_tiles; P.m_tiles = m_tiles; P.kb = kb; P.nq = n_this; P.n_groups = (int)(n_this_pad / 256);
+        P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores;
+        const int grid = std::min(P.n_groups, c->sm_count);
+        kern<<<grid, mma::THREADS, smem, c->stream>>>(map_a, map_b, P);
+        c->launches++;
+        if ((e = cudaMemsetAsync(flag.p, 0, sizeof(int32_t) * n_this, c->stream)) != cudaSuccess ||
+            (e = cudaMemsetAsync(flist.p + cq, 0, sizeof(int32_t), c->stream)) != cudaSuccess) {
+            set_error("search_mma memset: %s", cudaGetErrorString(e));
+            return done(GORSE_B200_ERR_CUDA);
+        }
+        const int pw = 4;
+        const size_t psm = (size_t)pw * mma::CAP * 8;
+        mma::prune_kernel<<<(unsigned)std::min<int64_t>((n_this + pw - 1) / pw, (int64_t)c->sm_count * 8), 32 * pw, psm, c->stream>>>(
+            ccol.p, cval.p, ccnt.p, theta.p, eps.p, ix->perm.p, qi, q0 + off, self_skip, n_this, k, ids.p, idcnt.p, flag.p);
+        c->launches++;
+        // stage 2: exact re-rank of the window, reference fp32 order
+        if ((st = launch_exact(ix, qp, qi, q0 + off, n_this, k, ids.p, idcnt.p, mma::CAP, nullptr, d_idx + off * k, d_dist + off * k, d_count + off,
+                               prune0, d_nan)))
+            return done(st);
+        // rows whose candidate set could not be certified: exact scan over everything
+        mma::compact_flags_kernel<<<(unsigned)((n_this + 255) / 256), 256, 0, c->stream>>>(flag.p, n_this, flist.p, flist.p + cq);
+        c->launches++;
+        int32_t n_fb = 0;
+        if ((e = cudaMemcpyAsync(&n_fb, flist.p + cq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+            (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
+            set_error("search_mma: %s", cudaGetErrorString(e));
+            return done(GORSE_B200_ERR_CUDA);
+        }
+        ix->last_fallback_rows += n_fb;
+        if (n_fb > 0) {
+            if ((st = launch_exact(ix, qp, qi, q0 + off, n_fb, k, nullptr, nullptr, 0, flist.p, d_idx + off * k, d_dist + off * k, d_count + off,
+                                   prune0, d_nan)))
+                return done(st);
+        }
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) { set_error("search_mma: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    return done(GORSE_B200_OK);
 }
 
 }  // namespace gb
