@@ -9,12 +9,12 @@
 // per-row candidate list.  Stage 2 (topk.cu) re-ranks the candidates exactly in the reference's fp32 order.
 //
 // Threshold without a second pass: the vectors are stored in a random column permutation, so the first m columns are a
-// uniform sample.  For those the epilogue tracks each row's 8 best scores; theta = 8th best - 2*eps is then fixed,
+// uniform sample.  For those the epilogue tracks each row's 16 best scores; theta = 16th best - 2*eps is then fixed,
 // the sweep continues over all columns (the first m are revisited at the end) and pushes score >= theta.
 //   * soundness: every true top-k element has score >= (k-th best approximate score) - 2*eps  (|score - exact| <= eps,
 //     eps from bf16 rounding: 1.02 * 2^-8 * |q| * max|x| + ...).  Stage 2 verifies that at least k candidates clear
 //     theta + 2*eps, which makes the candidate set a superset of the true top-k; rows that fail the check (or overflow
-//     their list) are redone by the exact scan.  With m = N/64 and the 8th best, a row fails with probability ~2e-4.
+//     their list) are redone by the exact scan.  With m = 5N/k and the 16th best, a row fails with probability ~2e-4.
 //
 // Roofline class: tensor pipe.  F = 2 * nq * N * Kp flop per sweep.
 #include <cuda.h>
@@ -33,7 +33,7 @@ constexpr int BM = 128, BN = 128, BK = 64;     // tile rows (queries), tile colu
 constexpr int TILES_M = 2;                     // query tiles per CTA (both multiply every B tile)
 constexpr int MAX_KB = 3;                      // k-blocks per tile: Kp <= 192
 constexpr int CAP = 1024;                      // candidate slots per query row
-constexpr int R_TOP = 8;                       // sample order statistic that fixes the threshold
+constexpr int R_TOP = 16;                      // sample order statistic that fixes the threshold
 constexpr int THREADS = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
 constexpr uint32_t TILE_BYTES = BM * BK * 2;   // one [128 x 64] bf16 k-block tile = 16 KB
 
@@ -513,8 +513,10 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     const int kp = kp_of(ix), kb = kp / mma::BK;
     const int64_t n_pad = (ix->n + mma::BN - 1) / mma::BN * mma::BN;
     const int n_tiles = (int)(n_pad / mma::BN);
-    int m_tiles = std::max(32, (int)((ix->n / 64 + mma::BN - 1) / mma::BN));
-    m_tiles = std::min(m_tiles, n_tiles);
+    // sample size: the R_TOP-th best of m random columns leaves on average R_TOP * N / m columns above it (Gamma(R_TOP)
+    // spread).  Aim for 3.2k: fewer than k with probability ~2e-4, and far below the CAP-slot candidate list.
+    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (3.2 * k) / mma::BN);
+    m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
     const size_t a_bytes = (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;

@@ -16,6 +16,22 @@ def ctx(gb):
     c.close()
 
 
+def assert_same_neighbours(idx, dist, oi, od):
+    """Distances bit-exact and ascending; ids identical wherever a distance is unique.  Exact fp32 ties (they do occur among
+    4*10^4 candidates) may come out in a different order: the reference's tie order is an artefact of Go's heap that no
+    reference test pins, ours is (distance, index).  Ids strictly inside the k-th distance must match as sets."""
+    assert dist.tobytes() == od.tobytes()
+    if idx.tolist() == oi.tolist():
+        return
+    last = od[-1]
+    for v in np.unique(od):
+        ours, theirs = set(idx[dist == v].tolist()), set(oi[od == v].tolist())
+        if v < last:
+            assert ours == theirs, (v, ours, theirs)
+        else:
+            assert len(ours) == len(theirs)
+
+
 def bf16_round(x):
     u = x.astype(np.float32).view(np.uint32).astype(np.uint64)
     u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
@@ -62,11 +78,15 @@ def test_tensor_path_equals_oracle(gb, orc, ctx, metric, d, k):
     assert fb <= 3, f"{fb} of {NQ} rows needed the exact fallback"
     oi, od, oc, _ = orc.bruteforce_all(X, 1000, 1000 + NQ, k, metric=om, n_threads=8)
     assert cnt.tolist() == oc.tolist()
-    assert idx.tolist() == oi.tolist()
-    assert dist.tobytes() == od.tobytes()
+    n_same = 0
+    for r in range(NQ):
+        assert_same_neighbours(idx[r, :cnt[r]], dist[r, :cnt[r]], oi[r, :oc[r]], od[r, :oc[r]])
+        n_same += idx[r].tolist() == oi[r].tolist()
+    assert n_same >= NQ - 10  # ties are rare
     for q in range(0, 128, 9):
         oi, od = orc.bruteforce_search(X, qv[q], k, prune0=(metric == "euclid"), metric=om)
-        assert cnt2[q] == len(oi) and idx2[q, :cnt2[q]].tolist() == oi.tolist() and dist2[q, :cnt2[q]].tobytes() == od.tobytes()
+        assert cnt2[q] == len(oi)
+        assert_same_neighbours(idx2[q, :cnt2[q]], dist2[q, :cnt2[q]], oi, od)
 
 
 def test_adversarial_inputs_fall_back_exactly(gb, orc, ctx):
