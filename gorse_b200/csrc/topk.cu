@@ -95,7 +95,8 @@ __device__ __forceinline__ void list_insert(float *ld, int32_t *li, int &len, in
 __global__ void __launch_bounds__(128)
 topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_ptr, const int64_t *q_idx, int64_t q0,
                   int64_t nq, int k, const int32_t *cand, const int32_t *cand_count, int cand_stride, const int32_t *row_list,
-                  int32_t *out_idx, float *out_dist, int32_t *out_count, int prune0, int *nan_flag)
+                  int32_t *out_idx, float *out_dist, int32_t *out_count, int prune0, int *nan_flag, int n_seg, int64_t seg_len,
+                  int cand_by_slot)
 {
     extern __shared__ unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -104,8 +105,13 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
     float *qs = reinterpret_cast<float *>(sm_raw) + (size_t)2 * nw * k + (size_t)wid * d;
     const int lane4 = lane & 3, quad = lane >> 2;
     const unsigned qmask = quad_mask();
+    // nq counts work slots: slot = (row_slot, segment).  With n_seg > 1 every slot scans one segment of the vectors and
+    // writes its own partial top-k at out[slot]; a second pass merges the partial lists (cand_by_slot) into out[row].
     for (int64_t slot = (int64_t)blockIdx.x * nw + wid; slot < nq; slot += (int64_t)gridDim.x * nw) {
-        const int64_t qi = row_list ? (int64_t)row_list[slot] : slot;
+        const int64_t row_slot = slot / n_seg;
+        const int seg = (int)(slot % n_seg);
+        const int64_t qi = row_list ? (int64_t)row_list[row_slot] : row_slot;
+        const int64_t oq = n_seg > 1 ? slot : qi;
         int64_t self = -1;
         const float *qsrc;
         if (q_ptr) qsrc = q_ptr + qi * d;
@@ -113,15 +119,17 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
         for (int e = lane; e < d; e += 32) qs[e] = qsrc[e];
         __syncwarp();
         int len = 0;
-        const int32_t *cl = cand ? cand + qi * cand_stride : nullptr;
-        const int64_t total = cand ? (int64_t)min(cand_count[qi], cand_stride) : N;
+        const int64_t cidx = cand_by_slot ? row_slot : qi;
+        const int32_t *cl = cand ? cand + cidx * cand_stride : nullptr;
+        const int64_t begin = cand ? 0 : (int64_t)seg * seg_len;
+        const int64_t total = cand ? (cand_count ? (int64_t)min(cand_count[cidx], cand_stride) : (int64_t)cand_stride) : min(N, begin + seg_len);
         if (d % 16 == 0 && d <= 256) {
             const int chunks = d / 16;
             float4 qreg[16];
 #pragma unroll
             for (int c = 0; c < 16; c++)
                 if (c < chunks) qreg[c] = *reinterpret_cast<const float4 *>(qs + 16 * c + 4 * lane4);
-            for (int64_t base = 0; base < total; base += 8) {
+            for (int64_t base = begin; base < total; base += 8) {
                 int64_t t = base + quad;
                 int64_t v = -1;
                 if (t < total) v = cl ? (int64_t)cl[t] : t;
@@ -141,7 +149,7 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
                 __syncwarp();
             }
         } else {
-            for (int64_t base = 0; base < total; base += 32) {
+            for (int64_t base = begin; base < total; base += 32) {
                 int64_t t = base + lane;
                 int64_t v = -1;
                 if (t < total) v = cl ? (int64_t)cl[t] : t;
@@ -170,10 +178,10 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
         int cnt = len - first;
         for (int e = lane; e < k; e += 32) {
             bool has = e < cnt;
-            out_idx[qi * k + e] = has ? li[first + e] : -1;
-            out_dist[qi * k + e] = has ? ld[first + e] : 0.f;
+            out_idx[oq * k + e] = has ? li[first + e] : -1;
+            out_dist[oq * k + e] = has ? ld[first + e] : 0.f;
         }
-        if (lane == 0) out_count[qi] = cnt;
+        if (lane == 0) out_count[oq] = cnt;
         __syncwarp();
     }
 }
@@ -189,9 +197,39 @@ int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qi
     GB_CUDA(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nq + warps - 1) / warps, (int64_t)c->sm_count * 8));
     topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, nq, k, d_cand,
-                                                         d_cand_count, cand_stride, row_list, d_idx, d_dist, d_count, prune0, d_nan);
+                                                         d_cand_count, cand_stride, row_list, d_idx, d_dist, d_count, prune0, d_nan, 1, ix->n, 0);
     GB_LAUNCHED(c);
     return GORSE_B200_OK;
+}
+
+// A few rows, each against ALL vectors (the tensor path's certified-fallback): split every row's scan into segments
+// handled by different warps (partial top-k per segment, no prune0 yet), then merge the partial lists exactly.
+int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int32_t n_rows, int k,
+                           const int32_t *row_list, int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan)
+{
+    gorse_b200_ctx *c = ix->ctx;
+    const int warps = 4;
+    size_t sm = (size_t)warps * (2 * (size_t)k * 4 + (size_t)ix->d * 4);
+    const int64_t seg_len = 4096;
+    const int n_seg = (int)((ix->n + seg_len - 1) / seg_len);
+    DevBuf<int32_t> p_idx, p_cnt;
+    DevBuf<float> p_dist;
+    int32_t st;
+    auto done = [&](int32_t s) { cudaStreamSynchronize(c->stream); p_idx.free(); p_cnt.free(); p_dist.free(); return s; };
+    const int64_t slots = (int64_t)n_rows * n_seg;
+    if ((st = p_idx.alloc((size_t)slots * k)) || (st = p_dist.alloc((size_t)slots * k)) || (st = p_cnt.alloc(slots))) return done(st);
+    GB_CUDA(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>((slots + warps - 1) / warps, (int64_t)c->sm_count * 16));
+    topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, slots, k, nullptr, nullptr, 0,
+                                                         row_list, p_idx.p, p_dist.p, p_cnt.p, 0, d_nan, n_seg, seg_len, 0);
+    c->launches++;
+    grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + warps - 1) / warps, (int64_t)c->sm_count * 8));
+    topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, n_rows, k, p_idx.p, nullptr,
+                                                         n_seg * k, row_list, d_idx, d_dist, d_count, prune0, d_nan, 1, ix->n, 1);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("exact fallback: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    return done(GORSE_B200_OK);
 }
 
 // run a search whose queries are already described by (d_q | d_qidx | q0); copies results to the host

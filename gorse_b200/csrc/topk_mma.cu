@@ -585,8 +585,7 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         }
         ix->last_fallback_rows += n_fb;
         if (n_fb > 0) {
-            if ((st = launch_exact(ix, qp, qi, q0 + off, n_fb, k, nullptr, nullptr, 0, flist.p, d_idx + off * k, d_dist + off * k, d_count + off,
-                                   prune0, d_nan)))
+            if ((st = launch_exact_split(ix, qp, qi, q0 + off, n_fb, k, flist.p, d_idx + off * k, d_dist + off * k, d_count + off, prune0, d_nan)))
                 return done(st);
         }
     }
