@@ -1,0 +1,58 @@
+"""The N > 1 plumbing of bench.py on CPU (gloo, world_size 2): rendezvous on 127.0.0.1, nccl-id broadcast buffer,
+max-over-ranks reduction, per-rank shard construction.  The CUDA/NCCL data path itself runs on the GPU box
+(tests/test_dist_gpu.py via torchrun)."""
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+import bench
+rank, world, local = bench.dist_env()
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# the 128-byte id travels from rank 0 to everyone
+idbuf = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    idbuf = torch.frombuffer(bytearray(range(128)), dtype=torch.uint8).clone()
+dist.broadcast(idbuf, 0)
+assert bytes(idbuf.numpy().tobytes()) == bytes(range(128))
+# weak-scaling shard: this rank's users are populated, the others' rows are empty
+bench.WORKLOADS["tiny"] = (300, 50, 2000, 16, "tiny")
+n_users, n_items, d, off, items = bench.make_shard("tiny", rank, world)
+assert n_users == 300 * world and 300 <= off[-1] == items.size <= 2000
+lo = rank * 300
+assert off[lo] == 0 and off[lo + 300] == items.size and np.all(np.diff(off[:lo + 1]) == 0) and np.all(np.diff(off[lo + 300:]) == 0)
+# max over ranks
+t = torch.tensor([float(rank + 1)], dtype=torch.float64)
+dist.all_reduce(t, op=dist.ReduceOp.MAX)
+assert t.item() == world
+dist.barrier()
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world2_plumbing(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_reference_arm_prints_contract_line():
+    env = dict(os.environ)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "small", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr
+    import json
+
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "triples/s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["cores"] >= 1
