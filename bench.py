@@ -318,13 +318,116 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_als(args):
+    """BASELINE configs[2]: eALS ("CCD") on the C2 data at d = 128; one step = one epoch (both half-sweeps + 2 Grams)."""
+    import gorse_b200 as gb
+    import oracle
+
+    U, I, R, d = (1_000_000, 100_000, 10_000_000, 128) if not args.small else (50_000, 10_000, 500_000, 128)
+    from gorse_b200 import synth
+    off, items = synth.make_feedback(U, I, R, seed=1000, zipf_s=ZIPF_S, exact=True)
+    ioff, iusers = gb.transpose_csr(off, items, I)
+    reg, alpha = 0.06, 0.001  # ALS defaults, model/cf/model.go:584-585
+    with gb.Context(0) as ctx, gb.CFModel(ctx, U, I, d, off, items, ioff, iusers) as m:
+        m.init_normal(0.0, 0.1, 0)
+        for _ in range(args.warmup):
+            m.als_epoch(reg, alpha)
+        sampler = ClockSampler(0)
+        l0, t0 = ctx.launch_count(), time.time()
+        ctx.timer_begin()
+        for _ in range(args.steps):
+            m.als_epoch(reg, alpha)
+        ms = ctx.timer_end() / args.steps
+        t1 = time.time()
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop(t0, t1)
+    peak, src = read_peaks()
+    nbytes = 2 * R * (4 * d + 4) + 3 * (U + I) * 4 * d
+    cb = None
+    if not args.no_cpu:
+        cores = len(os.sched_getaffinity(0))
+        Us, Is, Rs = 50_000, 10_000, 500_000
+        o2, i2 = synth.make_feedback(Us, Is, Rs, seed=1000, zipf_s=ZIPF_S, exact=True)
+        io2, iu2 = gb.transpose_csr(o2, i2, Is)
+        rng = np.random.default_rng(0)
+        P = (rng.standard_normal((Us, d)) * 0.1).astype(np.float32)
+        Q = (rng.standard_normal((Is, d)) * 0.1).astype(np.float32)
+        sec = oracle.als_epoch_threads(P, Q, o2, i2, io2, iu2, reg, alpha, cores)
+        cb = {"value": 2 * Rs / sec, "unit": "feedback visits/s", "cores": cores, "kind": "port",
+              "sample": f"one epoch at {Us} x {Is} x {Rs}, d={d}: rows over {cores} threads, serial Gram as in the reference, {sec:.2f} s"}
+    print(json.dumps({"metric": "eALS (CCD) feedback visits/sec", "value": 2 * R / (ms * 1e-3), "unit": "feedback visits/s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"eALS {U} users x {I} items x {R} feedback, d={d} (BASELINE configs[2])", "reg": reg, "alpha": alpha,
+                                 "item_popularity": f"zipf({ZIPF_S})"},
+                      "roofline": {"bound": "hbm", "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                   "frac": nbytes / (ms * 1e-3) / 1e9 / peak, "traffic": None, "algorithmic_bytes_per_epoch": nbytes,
+                                   "peak_source": src},
+                      "cpu_baseline": cb, "e2e": None, "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+
+
+def run_topk(args):
+    """BASELINE configs[3]: all-pairs top-100 over 1M x 128 unit vectors (cosine via -dot); value = query vectors/s."""
+    import gorse_b200 as gb
+    import oracle
+
+    N, d, k = (1_000_000, 128, 100) if not args.small else (100_000, 128, 100)
+    nq = min(N, args.queries)
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((N, d), dtype=np.float32)
+    X /= np.linalg.norm(X, axis=1, keepdims=True)
+    with gb.Context(0) as ctx, gb.BruteforceIndex(ctx, d, gb.METRIC_NEG_DOT) as ix:
+        ix.add(X)
+        ix.search_range(0, 512, k)  # builds the bf16 mirror
+        for _ in range(max(0, args.warmup - 1)):
+            ix.search_range(0, nq, k)
+        sampler = ClockSampler(0)
+        l0, t0 = ctx.launch_count(), time.time()
+        ms_list = []
+        for s in range(args.steps):
+            ctx.timer_begin()
+            idx, dist, cnt = ix.search_range(0, nq, k)   # host buffers out: this IS the end-to-end call
+            ms_list.append(ctx.timer_end())
+        t1 = time.time()
+        launches = ctx.launch_count() - l0
+        fb = ix.debug_fallback_rows()
+        clocks = sampler.stop(t0, t1)
+    ms = float(np.mean(ms_list))
+    assert cnt.min() == k
+    flop = 2.0 * nq * N * d
+    peak = 1427.2
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peak = float(json.load(open(pp)).get("bf16_tflops_sustained", peak))
+    cb = None
+    if not args.no_cpu:
+        cores = len(os.sched_getaffinity(0))
+        sample = 4 * cores
+        _, _, _, sec = oracle.bruteforce_all(X, 0, sample, k, metric=oracle.METRIC_NEG_DOT, n_threads=cores)
+        cb = {"value": sample / sec, "unit": "vectors/s", "cores": cores, "kind": "port",
+              "sample": f"{sample} queries of the same 1M set: reference-order dot + Go heap per query, {cores} threads, {sec:.2f} s"}
+    print(json.dumps({"metric": "item-to-item top-k vectors/sec", "value": nq / (ms * 1e-3), "unit": "vectors/s", "n_gpus": 1, "steps": args.steps,
+                      "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": "bf16 tensor-core candidate generation + f32 exact re-rank", "data": "synthetic",
+                      "config": {"workload": f"all-pairs top-{k} over {N} x {d} unit vectors, {nq} query rows per step (BASELINE configs[3])",
+                                 "metric": "-dot (cosine on unit vectors)", "fallback_rows": int(fb)},
+                      "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": flop / (ms * 1e-3) / 1e12 / peak, "traffic": None,
+                                   "note": "whole search call (mirror queries, tcgen05 sweep, prune, exact re-rank, result D2H); algorithmic flop 2*nq*N*d"},
+                      "cpu_baseline": cb, "e2e": {"value": nq / (ms * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": 0,
+                                                  "d2h_bytes_per_step": nq * k * 8 + nq * 4},
+                      "gpu_launches": int(launches), "clocks": clocks}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4"])
+    ap.add_argument("--small", action="store_true", help="c3/c4 at reduced size (not a bench number)")
+    ap.add_argument("--queries", type=int, default=151552, help="c4: query rows per step")
     ap.add_argument("--scatter", default="atomic", choices=["atomic", "store"])
     ap.add_argument("--e2e-epochs", type=int, default=E2E_EPOCHS)
     ap.add_argument("--zipf", type=float, default=None, help="item popularity exponent of the synthetic data (default 1.0; 0 = uniform)")
@@ -335,7 +438,11 @@ def main():
         global ZIPF_S
         ZIPF_S = args.zipf
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
+    if args.workload == "c3":
+        run_als(args)
+    elif args.workload == "c4":
+        run_topk(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

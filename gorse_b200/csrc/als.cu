@@ -206,6 +206,111 @@ als_rows_kernel(float *X, const float *Y, int d, int32_t x_lo, int32_t y_lo, con
     }
 }
 
+// ---- Gram form for rows too long to stage ---------------------------------------------------
+// eALS over f for one row is exactly one Gauss-Seidel sweep on  A x = h  with
+//     A = (1-w) * G + w * S + reg * I,   G = sum_{t in R} y_t y_t^T,   h = sum_{t in R} y_t
+// (a = h_f - (1-w) sum_{k!=f} x_k G[k][f],  b = w sum_{k!=f} x_k S[k][f],  c = (1-w) G[f][f]; model.go:666-680).
+// A long row is cut into chunks of <= GB_ALS_CHUNK entries; each CTA turns one chunk into a partial (G, h) with the
+// same 16x16-thread register tiling as gram_kernel, and one CTA per row sums the partials and does the sweep.
+#define GB_ALS_CHUNK 2048
+
+template <int T>
+__global__ void __launch_bounds__(256) als_chunk_gram_kernel(const float *Y, int d, const int32_t *idx, const int32_t *chunk_row,
+                                                             const int64_t *chunk_begin, const int32_t *chunk_len, float *partial)
+{
+    extern __shared__ float xs[];  // [16][dp]
+    const int dp = 16 * T;
+    const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
+    float acc[T][T], hacc[T];
+#pragma unroll
+    for (int a = 0; a < T; a++) {
+        hacc[a] = 0.f;
+#pragma unroll
+        for (int b = 0; b < T; b++) acc[a][b] = 0.f;
+    }
+    const int64_t b0 = chunk_begin[blockIdx.x];
+    const int len = chunk_len[blockIdx.x];
+    for (int base = 0; base < len; base += 16) {
+        for (int e = threadIdx.x; e < 16 * dp; e += 256) {
+            int rr = e / dp, k = e - rr * dp;
+            float v = 0.f;
+            if (base + rr < len && k < d) v = __ldg(Y + (int64_t)__ldg(idx + b0 + base + rr) * d + k);
+            xs[e] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < 16; rr++) {
+            float a[T], b[T];
+#pragma unroll
+            for (int k = 0; k < T; k++) { a[k] = xs[rr * dp + ti * T + k]; b[k] = xs[rr * dp + tj * T + k]; }
+#pragma unroll
+            for (int x = 0; x < T; x++)
+#pragma unroll
+                for (int y = 0; y < T; y++) acc[x][y] = __fmaf_rn(a[x], b[y], acc[x][y]);
+            if (ti == 0) {
+#pragma unroll
+                for (int y = 0; y < T; y++) hacc[y] += b[y];
+            }
+        }
+        __syncthreads();
+    }
+    float *out = partial + (int64_t)blockIdx.x * (d * d + d);
+#pragma unroll
+    for (int x = 0; x < T; x++)
+#pragma unroll
+        for (int y = 0; y < T; y++) {
+            int i = ti * T + x, j = tj * T + y;
+            if (i < d && j < d) out[i * d + j] = acc[x][y];
+        }
+    if (ti == 0) {
+#pragma unroll
+        for (int y = 0; y < T; y++) if (tj * T + y < d) out[d * d + tj * T + y] = hacc[y];
+    }
+}
+
+// one CTA per long row: sum its chunk partials in order (deterministic), build A, one Gauss-Seidel sweep by warp 0
+__global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const float *S, float reg, float w, const int32_t *rows,
+                                                        const int32_t *row_chunk0, const float *partial)
+{
+    extern __shared__ float sm[];
+    float *A = sm;                 // [d][d+1]
+    float *h = A + d * (d + 1);    // [d]
+    float *x = h + d;              // [d]
+    const int r = rows[blockIdx.x];
+    const int c0 = row_chunk0[blockIdx.x], c1 = row_chunk0[blockIdx.x + 1];
+    const int dd = d * d, stride = dd + d;
+    const float omw = 1.0f - w;
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        float g = 0.f;
+        for (int c = c0; c < c1; c++) g += partial[(int64_t)c * stride + e];
+        const int i = e / d, j = e - i * d;
+        float a = omw * g + w * __ldg(S + e);
+        if (i == j) a += reg;
+        A[i * (d + 1) + j] = a;
+    }
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {
+        float g = 0.f;
+        for (int c = c0; c < c1; c++) g += partial[(int64_t)c * stride + dd + e];
+        h[e] = g;
+        x[e] = X[(int64_t)r * d + e];
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        for (int f = 0; f < d; f++) {
+            float s = 0.f;
+            for (int k = lane; k < d; k += 32)
+                if (k != f) s += x[k] * A[f * (d + 1) + k];   // A is symmetric: row f instead of column f
+            s = warp_sum(s);
+            const float xn = (h[f] - s) / A[f * (d + 1) + f];
+            __syncwarp();
+            if (lane == 0) x[f] = xn;
+            __syncwarp();
+        }
+        for (int k = lane; k < d; k += 32) X[(int64_t)r * d + k] = x[k];
+    }
+}
+
 static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const int64_t *off)
 {
     gorse_b200_ctx *c = cf->ctx;
@@ -261,6 +366,39 @@ static int32_t prepare_als(gorse_b200_cf *cf)
                 GB_CUDA(cudaMemcpy(cf->als_rows[side][k].p, cls[k].data(), sizeof(int32_t) * cls[k].size(), cudaMemcpyHostToDevice));
         }
     }
+    // long rows (class 2) take the Gram form when d <= 128: cut them into chunks
+    for (int side = 0; side < 2 && cf->d <= 128; side++) {
+        const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
+        std::vector<int32_t> rows((size_t)cf->als_rows_n[side][2]);
+        if (rows.empty()) continue;
+        GB_CUDA(cudaMemcpy(rows.data(), cf->als_rows[side][2].p, sizeof(int32_t) * rows.size(), cudaMemcpyDeviceToHost));
+        std::vector<int32_t> chunk_row, chunk_len, row_chunk0;
+        std::vector<int64_t> chunk_begin;
+        for (size_t i = 0; i < rows.size(); i++) {
+            row_chunk0.push_back((int32_t)chunk_row.size());
+            const int64_t b = off[(size_t)rows[i]], e = off[(size_t)rows[i] + 1];
+            for (int64_t p = b; p < e; p += GB_ALS_CHUNK) {
+                chunk_row.push_back(rows[i]);
+                chunk_begin.push_back(p);
+                chunk_len.push_back((int32_t)std::min<int64_t>(GB_ALS_CHUNK, e - p));
+            }
+        }
+        row_chunk0.push_back((int32_t)chunk_row.size());
+        cf->als_n_chunks[side] = (int32_t)chunk_row.size();
+        GB_TRY(cf->als_chunk_row[side].alloc(chunk_row.size()));
+        GB_TRY(cf->als_chunk_len[side].alloc(chunk_len.size()));
+        GB_TRY(cf->als_chunk_begin[side].alloc(chunk_begin.size()));
+        GB_TRY(cf->als_row_chunk0[side].alloc(row_chunk0.size()));
+        GB_CUDA(cudaMemcpy(cf->als_chunk_row[side].p, chunk_row.data(), sizeof(int32_t) * chunk_row.size(), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemcpy(cf->als_chunk_len[side].p, chunk_len.data(), sizeof(int32_t) * chunk_len.size(), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemcpy(cf->als_chunk_begin[side].p, chunk_begin.data(), sizeof(int64_t) * chunk_begin.size(), cudaMemcpyHostToDevice));
+        GB_CUDA(cudaMemcpy(cf->als_row_chunk0[side].p, row_chunk0.data(), sizeof(int32_t) * row_chunk0.size(), cudaMemcpyHostToDevice));
+    }
+    {
+        const size_t need = (size_t)std::max(cf->als_n_chunks[0], cf->als_n_chunks[1]) * ((size_t)cf->d * cf->d + cf->d);
+        if (need) GB_TRY(cf->als_partial.alloc(need));
+    }
+    GB_CUDA(cudaFuncSetAttribute(als_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GB_TRY(cf->gram.alloc((size_t)cf->d * cf->d));
     GB_CUDA(cudaFuncSetAttribute(als_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     cf->als_ready = true;
@@ -274,6 +412,22 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
     for (int k = 0; k < 3; k++) {
         int32_t n_rows = cf->als_rows_n[side][k];
         if (n_rows == 0) continue;
+        if (k == 2 && cf->als_n_chunks[side] > 0) {
+            const int d = cf->d, T = d <= 16 ? 1 : d <= 32 ? 2 : d <= 64 ? 4 : 8;
+            const size_t gsm = sizeof(float) * 16 * 16 * T;
+            const int nc = cf->als_n_chunks[side];
+            switch (T) {
+                case 1: als_chunk_gram_kernel<1><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
+                case 2: als_chunk_gram_kernel<2><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
+                case 4: als_chunk_gram_kernel<4><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
+                default: als_chunk_gram_kernel<8><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
+            }
+            GB_LAUNCHED(c);
+            const size_t ssm = sizeof(float) * ((size_t)d * (d + 1) + 2 * d);
+            als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, cf->als_rows[side][2].p, cf->als_row_chunk0[side].p, cf->als_partial.p);
+            GB_LAUNCHED(c);
+            continue;
+        }
         size_t sm = sizeof(float) * GB_ALS_WARPS * (size_t)(cf->d + kStageFloats[k]);
         int ctas_per_sm = k == 0 ? 4 : 1;
         int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + GB_ALS_WARPS - 1) / GB_ALS_WARPS, (int64_t)c->sm_count * ctas_per_sm * (k == 2 ? 8 : 1)));

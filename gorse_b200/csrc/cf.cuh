@@ -54,6 +54,11 @@ struct gorse_b200_cf {
     gb::DevBuf<int32_t> als_rows[2][3];  // [side][class] row ids bucketed by length (built lazily)
     int32_t als_rows_n[2][3] = {{0, 0, 0}, {0, 0, 0}};
     bool als_ready = false;
+    // long rows in Gram form: chunk work list per side and the partial (G, h) scratch
+    int32_t als_n_chunks[2] = {0, 0};
+    gb::DevBuf<int32_t> als_chunk_row[2], als_chunk_len[2], als_row_chunk0[2];
+    gb::DevBuf<int64_t> als_chunk_begin[2];
+    gb::DevBuf<float> als_partial;
     std::vector<int64_t> h_user_off, h_item_off;  // host copies of the offsets (bucketing, wave building)
 };
 
