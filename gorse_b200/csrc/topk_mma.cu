@@ -32,9 +32,11 @@ namespace mma {
 constexpr int BM = 128, BN = 128, BK = 64;     // tile rows (queries), tile columns (vectors), k-block (bf16 elements)
 constexpr int TILES_M = 2;                     // query tiles per CTA (both multiply every B tile)
 constexpr int MAX_KB = 3;                      // k-blocks per tile: Kp <= 192
-constexpr int CAP = 1024;                      // candidate slots per query row
+constexpr int CAP = 2048;                      // candidate slots per query row
 constexpr int R_TOP = 16;                      // sample order statistic that fixes the threshold
-constexpr int THREADS = 384;                   // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..11 epilogue
+constexpr int EPI_WARPS = 16;                  // 2 query tiles x 4 lane quarters x 2 column halves
+constexpr int HALF_CAP = CAP / 2;              // candidate slots per (row, column half)
+constexpr int THREADS = 128 + 32 * EPI_WARPS;  // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..19 epilogue
 constexpr uint32_t TILE_BYTES = BM * BK * 2;   // one [128 x 64] bf16 k-block tile = 16 KB
 
 __device__ __forceinline__ uint32_t s32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,8 +115,8 @@ struct Params {
     const float *eps;     // [nq] error margin per query row
     int32_t *cand_col;    // [nq][CAP] permuted column index
     float *cand_val;      // [nq][CAP]
-    int32_t *cand_cnt;    // [nq] pushes (may exceed CAP)
-    float *theta;         // [nq] threshold used
+    int32_t *cand_cnt;    // [nq][2] pushes per column half (may exceed HALF_CAP)
+    float *theta;         // [nq][2] threshold used by each half
     float *dbg;           // optional dense [nq][n_tiles*128] score dump (tests)
 };
 
@@ -139,7 +141,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 8); }
+        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -200,8 +202,10 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: 8 warps = 2 query tiles x 128 rows, one thread per row =====
-        const int ew = warp - 4, m = ew >> 2;
+        // ===== epilogue: 16 warps = 2 query tiles x 4 lane quarters x 2 column halves.  A (row, half) pair is one thread:
+        // it samples, thresholds and pushes on its own 64 of every 128 columns (its theta comes from its half of the
+        // sample, a valid if slightly looser bound), so the two halves never synchronise.
+        const int ew = warp - 4, m = ew >> 3, half = (ew >> 2) & 1;
         const uint32_t lane_base = (uint32_t)((ew & 3) * 32) << 16;  // a warp may only touch its own 32 TMEM lanes
         uint32_t at = 0;
         for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
@@ -213,8 +217,8 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int r = 0; r < R_TOP; r++) top[r] = -INFINITY;
             float theta = -INFINITY;
             int cnt = 0;
-            int32_t *ccol = P.cand_col + (row_ok ? row : 0) * CAP;
-            float *cval = P.cand_val + (row_ok ? row : 0) * CAP;
+            int32_t *ccol = P.cand_col + (row_ok ? row : 0) * CAP + half * HALF_CAP;
+            float *cval = P.cand_val + (row_ok ? row : 0) * CAP + half * HALF_CAP;
             for (int t = 0; t < total_tiles; t++, at++) {
                 const int as = at & 1;
                 const bool sample = t < P.m_tiles;
@@ -224,7 +228,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t acc = tmem_base + lane_base + (uint32_t)((m * 2 + as) * BN);
 #pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
+                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
                     __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the data-dependent pushes
                     tmem_ld32(acc + c0, v);
@@ -259,7 +263,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 for (int f = 0; f < 4; f++) {
                                     const float x = __uint_as_float(v[e + f]);
                                     if (x >= theta && col0 + e + f < P.n && row_ok) {
-                                        if (cnt < CAP) { ccol[cnt] = (int32_t)(col0 + e + f); cval[cnt] = x; }
+                                        if (cnt < HALF_CAP) { ccol[cnt] = (int32_t)(col0 + e + f); cval[cnt] = x; }
                                         cnt++;
                                     }
                                 }
@@ -271,7 +275,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&t_empty[as]);
             }
-            if (row_ok) { P.cand_cnt[row] = cnt; P.theta[row] = theta; }
+            if (row_ok) { P.cand_cnt[2 * row + half] = cnt; P.theta[2 * row + half] = theta; }
         }
     }
     __syncthreads();
@@ -369,19 +373,23 @@ prune_kernel(const int32_t *cand_col, const float *cand_val, const int32_t *cand
     float *sv = reinterpret_cast<float *>(sm) + (size_t)warp * mma::CAP;
     int32_t *sc = reinterpret_cast<int32_t *>(reinterpret_cast<float *>(sm) + (size_t)nw * mma::CAP) + (size_t)warp * mma::CAP;
     for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < nq; row += (int64_t)gridDim.x * nw) {
-        const int raw = cand_cnt[row];
+        const int raw0 = cand_cnt[2 * row], raw1 = cand_cnt[2 * row + 1];
+        const int n0 = min(raw0, mma::HALF_CAP), n1 = min(raw1, mma::HALF_CAP);
+        // every column with score >= max(theta_0, theta_1) was pushed by one of the two halves
+        const float th = fmaxf(theta[2 * row], theta[2 * row + 1]);
         int32_t *oi = out_ids + row * mma::CAP;
         const int64_t self = self_skip ? (q_idx ? q_idx[row] : q0 + row) : -1;
-        bool bad = raw > mma::CAP || !(eps[row] == eps[row]) || !(theta[row] == theta[row]);
-        const int n = min(raw, mma::CAP);
+        bool bad = raw0 > mma::HALF_CAP || raw1 > mma::HALF_CAP || !(eps[row] == eps[row]) || !(th == th);
+        const int n = n0 + n1;
         int np2 = 32;
         while (np2 < n) np2 <<= 1;
         for (int e = lane; e < np2; e += 32) {
             float v = -INFINITY;
             int32_t c = -1;
             if (e < n) {
-                c = perm[cand_col[row * mma::CAP + e]];  // original id
-                v = cand_val[row * mma::CAP + e];
+                const int64_t src = row * mma::CAP + (e < n0 ? e : mma::HALF_CAP + (e - n0));
+                c = perm[cand_col[src]];  // original id
+                v = cand_val[src];
                 if (c == self) v = -INFINITY;            // SearchIndex never returns the query itself
             }
             sv[e] = v;
@@ -403,7 +411,7 @@ prune_kernel(const int32_t *cand_col, const float *cand_val, const int32_t *cand
         int w = 0;
         if (!bad) {
             const int have = n - (self >= 0 ? 1 : 0);  // upper bound; -inf entries sort last anyway
-            if (have < k || !(sv[k - 1] >= theta[row] + two_eps)) bad = true;
+            if (have < k || !(sv[k - 1] >= th + two_eps)) bad = true;
         }
         if (!bad) {
             const float lim = sv[k - 1] - two_eps;
@@ -538,8 +546,8 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         return s;
     };
     const int64_t cq = std::min(nq, chunk), cq_pad = (cq + 255) / 256 * 256;
-    if ((st = Qb.alloc((size_t)cq_pad * kp)) || (st = eps.alloc(cq)) || (st = cval.alloc((size_t)cq * mma::CAP)) || (st = theta.alloc(cq)) ||
-        (st = ccol.alloc((size_t)cq * mma::CAP)) || (st = ccnt.alloc(cq)) || (st = ids.alloc((size_t)cq * mma::CAP)) || (st = idcnt.alloc(cq)) ||
+    if ((st = Qb.alloc((size_t)cq_pad * kp)) || (st = eps.alloc(cq)) || (st = cval.alloc((size_t)cq * mma::CAP)) || (st = theta.alloc(2 * cq)) ||
+        (st = ccol.alloc((size_t)cq * mma::CAP)) || (st = ccnt.alloc(2 * cq)) || (st = ids.alloc((size_t)cq * mma::CAP)) || (st = idcnt.alloc(cq)) ||
         (st = flag.alloc(cq)) || (st = flist.alloc(cq + 1)))
         return done(st);
     auto kern = stages >= 4 ? mma::topk_mma_kernel<4> : stages == 3 ? mma::topk_mma_kernel<3> : mma::topk_mma_kernel<2>;
@@ -567,6 +575,10 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         }
         const int pw = 4;
         const size_t psm = (size_t)pw * mma::CAP * 8;
+        if ((e = cudaFuncSetAttribute(mma::prune_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm)) != cudaSuccess) {
+            set_error("prune smem attr: %s", cudaGetErrorString(e));
+            return done(GORSE_B200_ERR_CUDA);
+        }
         mma::prune_kernel<<<(unsigned)std::min<int64_t>((n_this + pw - 1) / pw, (int64_t)c->sm_count * 8), 32 * pw, psm, c->stream>>>(
             ccol.p, cval.p, ccnt.p, theta.p, eps.p, ix->perm.p, qi, q0 + off, self_skip, n_this, k, ids.p, idcnt.p, flag.p);
         c->launches++;
