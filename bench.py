@@ -382,6 +382,7 @@ def run_topk(args):
         for _ in range(max(0, args.warmup - 1)):
             ix.search_range(0, nq, k)
         sampler = ClockSampler(0)
+        ix.debug_stage1()
         l0, t0 = ctx.launch_count(), time.time()
         ms_list = []
         for s in range(args.steps):
@@ -391,6 +392,7 @@ def run_topk(args):
         t1 = time.time()
         launches = ctx.launch_count() - l0
         fb = ix.debug_fallback_rows()
+        s1_ms, s1_flop = ix.debug_stage1()
         clocks = sampler.stop(t0, t1)
     ms = float(np.mean(ms_list))
     assert cnt.min() == k
@@ -411,9 +413,12 @@ def run_topk(args):
                       "dtype": "bf16 tensor-core candidate generation + f32 exact re-rank", "data": "synthetic",
                       "config": {"workload": f"all-pairs top-{k} over {N} x {d} unit vectors, {nq} query rows per step (BASELINE configs[3])",
                                  "metric": "-dot (cosine on unit vectors)", "fallback_rows": int(fb)},
-                      "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
-                                   "frac": flop / (ms * 1e-3) / 1e12 / peak, "traffic": None,
-                                   "note": "whole search call (mirror queries, tcgen05 sweep, prune, exact re-rank, result D2H); algorithmic flop 2*nq*N*d"},
+                      "roofline": {"bound": "tensor", "achieved": s1_flop / (s1_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
+                                   "frac": s1_flop / (s1_ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "mma::topk_mma_kernel<4>",
+                                   "kernel_ms": s1_ms / args.steps, "algorithmic_flop_per_launch": s1_flop / args.steps,
+                                   "whole_call_tflops": flop / (ms * 1e-3) / 1e12,
+                                   "note": "dominant kernel = the tcgen05 sweep (CUDA events on the library's stream); algorithmic flop 2*nq*N*d; "
+                                           "peak = measured sustained bf16 (MEASURED_PEAKS.json). whole_call adds query mirror, prune, exact re-rank, fallback and result D2H"},
                       "cpu_baseline": cb, "e2e": {"value": nq / (ms * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": 0,
                                                   "d2h_bytes_per_step": nq * k * 8 + nq * 4},
                       "gpu_launches": int(launches), "clocks": clocks}), flush=True)

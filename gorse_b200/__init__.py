@@ -243,6 +243,14 @@ class BruteforceIndex:
         check(raw.gorse_b200_debug_topk_fallback_rows(self.h, C.byref(n)))
         return n.value
 
+    def debug_stage1(self):
+        """(device ms, algorithmic flop) of the tcgen05 stage-1 kernel since the last call."""
+        ms, fl = C.c_double(0), C.c_double(0)
+        raw = C.CDLL(_lib.LIB_PATH)
+        raw.gorse_b200_debug_topk_stage1.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        check(raw.gorse_b200_debug_topk_stage1(self.h, C.byref(ms), C.byref(fl)))
+        return ms.value, fl.value
+
     def debug_stage1_scores(self, q0, q1):
         out = np.zeros((q1 - q0, len(self)), np.float32)
         raw = C.CDLL(_lib.LIB_PATH)

@@ -318,6 +318,9 @@ int32_t gorse_b200_index_destroy(gorse_b200_index *ix)
     ix->Xb.free();
     ix->norm.free();
     ix->perm.free();
+    if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
+    ix->w_qb.free(); ix->w_eps.free(); ix->w_cval.free(); ix->w_theta.free();
+    ix->w_ccol.free(); ix->w_ccnt.free(); ix->w_ids.free(); ix->w_idcnt.free(); ix->w_flag.free(); ix->w_flist.free();
     delete ix;
     return GORSE_B200_OK;
 }
@@ -400,6 +403,16 @@ int32_t gorse_b200_debug_topk_fallback_rows(gorse_b200_index *ix, int64_t *rows)
     GB_CHECK_ARG(ix != nullptr && rows != nullptr, "NULL argument");
     *rows = ix->last_fallback_rows;
     ix->last_fallback_rows = 0;
+    return GORSE_B200_OK;
+}
+
+// device time and algorithmic flop (2 * nq * N * d) of the stage-1 tensor-core kernel since the last call
+int32_t gorse_b200_debug_topk_stage1(gorse_b200_index *ix, double *ms, double *flop)
+{
+    GB_CHECK_ARG(ix != nullptr && ms != nullptr && flop != nullptr, "NULL argument");
+    *ms = ix->stage1_ms;
+    *flop = ix->stage1_flop;
+    ix->stage1_ms = ix->stage1_flop = 0.0;
     return GORSE_B200_OK;
 }
 

@@ -16,6 +16,14 @@ struct gorse_b200_index {
     bool mma_ready = false;
     float *dbg_scores = nullptr;    // tests only: dense stage-1 scores
     int64_t last_fallback_rows = 0; // rows of the last searches that needed the exact scan
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // CUDA events around the stage-1 kernel (bench.py roofline)
+    double stage1_ms = 0.0, stage1_flop = 0.0; // accumulated since the last debug read
+    // reusable work buffers of the tensor path (sized for w_cq query rows at mirror width w_kp)
+    int64_t w_cq = 0;
+    int w_kp = 0;
+    gb::DevBuf<__nv_bfloat16> w_qb;
+    gb::DevBuf<float> w_eps, w_cval, w_theta;
+    gb::DevBuf<int32_t> w_ccol, w_ccnt, w_ids, w_idcnt, w_flag, w_flist;
     std::mutex mu;
 };
 

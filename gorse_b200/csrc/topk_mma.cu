@@ -536,20 +536,24 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
     // queries are processed in chunks so that the candidate lists stay modest
     const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM * 4;
-    DevBuf<__nv_bfloat16> Qb;
-    DevBuf<float> eps, cval, theta;
-    DevBuf<int32_t> ccol, ccnt, ids, idcnt, flag, flist;
+    // work buffers live in the index and are reused by later searches (multi-GB cudaMalloc/cudaFree per call otherwise)
+    DevBuf<__nv_bfloat16> &Qb = ix->w_qb;
+    DevBuf<float> &eps = ix->w_eps, &cval = ix->w_cval, &theta = ix->w_theta;
+    DevBuf<int32_t> &ccol = ix->w_ccol, &ccnt = ix->w_ccnt, &ids = ix->w_ids, &idcnt = ix->w_idcnt, &flag = ix->w_flag, &flist = ix->w_flist;
     int32_t st = GORSE_B200_OK;
     auto done = [&](int32_t s) {
         cudaStreamSynchronize(c->stream);
-        Qb.free(); eps.free(); cval.free(); theta.free(); ccol.free(); ccnt.free(); ids.free(); idcnt.free(); flag.free(); flist.free();
         return s;
     };
     const int64_t cq = std::min(nq, chunk), cq_pad = (cq + 255) / 256 * 256;
-    if ((st = Qb.alloc((size_t)cq_pad * kp)) || (st = eps.alloc(cq)) || (st = cval.alloc((size_t)cq * mma::CAP)) || (st = theta.alloc(2 * cq)) ||
+    if (ix->w_cq >= cq && ix->w_kp == kp) {
+        // reuse
+    } else if ((ix->w_cq = 0, false) || (st = Qb.alloc((size_t)cq_pad * kp)) || (st = eps.alloc(cq)) || (st = cval.alloc((size_t)cq * mma::CAP)) || (st = theta.alloc(2 * cq)) ||
         (st = ccol.alloc((size_t)cq * mma::CAP)) || (st = ccnt.alloc(2 * cq)) || (st = ids.alloc((size_t)cq * mma::CAP)) || (st = idcnt.alloc(cq)) ||
         (st = flag.alloc(cq)) || (st = flist.alloc(cq + 1)))
         return done(st);
+    else { ix->w_cq = cq; ix->w_kp = kp; }
+    const int64_t fl_off = ix->w_cq;  // the fallback counter sits after the list
     auto kern = stages >= 4 ? mma::topk_mma_kernel<4> : stages == 3 ? mma::topk_mma_kernel<3> : mma::topk_mma_kernel<2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("search_mma smem attr: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
@@ -566,10 +570,13 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         P.n = ix->n; P.n_tiles = n_tiles; P.m_tiles = m_tiles; P.kb = kb; P.nq = n_this; P.n_groups = (int)(n_this_pad / 256);
         P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores;
         const int grid = std::min(P.n_groups, c->sm_count);
+        if (!ix->ev0) { cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1); }
+        cudaEventRecord(ix->ev0, c->stream);
         kern<<<grid, mma::THREADS, smem, c->stream>>>(map_a, map_b, P);
+        cudaEventRecord(ix->ev1, c->stream);
         c->launches++;
         if ((e = cudaMemsetAsync(flag.p, 0, sizeof(int32_t) * n_this, c->stream)) != cudaSuccess ||
-            (e = cudaMemsetAsync(flist.p + cq, 0, sizeof(int32_t), c->stream)) != cudaSuccess) {
+            (e = cudaMemsetAsync(flist.p + fl_off, 0, sizeof(int32_t), c->stream)) != cudaSuccess) {
             set_error("search_mma memset: %s", cudaGetErrorString(e));
             return done(GORSE_B200_ERR_CUDA);
         }
@@ -587,15 +594,19 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
                                prune0, d_nan)))
             return done(st);
         // rows whose candidate set could not be certified: exact scan over everything
-        mma::compact_flags_kernel<<<(unsigned)((n_this + 255) / 256), 256, 0, c->stream>>>(flag.p, n_this, flist.p, flist.p + cq);
+        mma::compact_flags_kernel<<<(unsigned)((n_this + 255) / 256), 256, 0, c->stream>>>(flag.p, n_this, flist.p, flist.p + fl_off);
         c->launches++;
         int32_t n_fb = 0;
-        if ((e = cudaMemcpyAsync(&n_fb, flist.p + cq, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+        if ((e = cudaMemcpyAsync(&n_fb, flist.p + fl_off, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
             (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
             set_error("search_mma: %s", cudaGetErrorString(e));
             return done(GORSE_B200_ERR_CUDA);
         }
         ix->last_fallback_rows += n_fb;
+        {
+            float ms = 0.f;  // the stream was synchronised just above
+            if (cudaEventElapsedTime(&ms, ix->ev0, ix->ev1) == cudaSuccess) { ix->stage1_ms += ms; ix->stage1_flop += 2.0 * (double)n_this * (double)ix->n * (double)ix->d; }
+        }
         if (n_fb > 0) {
             if ((st = launch_exact_split(ix, qp, qi, q0 + off, n_fb, k, flist.p, d_idx + off * k, d_dist + off * k, d_count + off, prune0, d_nan)))
                 return done(st);
