@@ -22,7 +22,7 @@
 namespace gb {
 
 #define GB_HOTQ_REGIONS 64      // independent append counters (one per group of warps)
-#define GB_HOT_ROW_CONCURRENCY 512   // most triples of one hot item in flight at any time
+#define GB_HOT_ROW_CONCURRENCY 768   // most triples of one hot item in flight at any time (at lr = 0.05; scaled by 0.05/lr)
 #define GB_HOT_SLOT_FLOATS 32        // one 128-byte line per 16-byte piece of a hot row
 
 struct HotQueue {
