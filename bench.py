@@ -379,15 +379,18 @@ def run_topk(args):
     with gb.Context(0) as ctx, gb.BruteforceIndex(ctx, d, gb.METRIC_NEG_DOT) as ix:
         ix.add(X)
         ix.search_range(0, 512, k)  # builds the bf16 mirror
+        # results land in page-locked host buffers, like the shim's pinned mirror (gorse_b200_host_alloc)
+        pin = (gb.PinnedArray((nq, k), np.int32), gb.PinnedArray((nq, k), np.float32), gb.PinnedArray((nq,), np.int32))
+        out = (pin[0].array, pin[1].array, pin[2].array)
         for _ in range(max(0, args.warmup - 1)):
-            ix.search_range(0, nq, k)
+            ix.search_range(0, nq, k, out=out)
         sampler = ClockSampler(0)
         ix.debug_stage1()
         l0, t0 = ctx.launch_count(), time.time()
         ms_list = []
         for s in range(args.steps):
             ctx.timer_begin()
-            idx, dist, cnt = ix.search_range(0, nq, k)   # host buffers out: this IS the end-to-end call
+            idx, dist, cnt = ix.search_range(0, nq, k, out=out)   # host buffers out: this IS the end-to-end call
             ms_list.append(ctx.timer_end())
         t1 = time.time()
         launches = ctx.launch_count() - l0
@@ -396,6 +399,9 @@ def run_topk(args):
         clocks = sampler.stop(t0, t1)
     ms = float(np.mean(ms_list))
     assert cnt.min() == k
+    cnt = None
+    for p_ in pin:
+        p_.free()
     flop = 2.0 * nq * N * d
     peak = 1427.2
     pp = os.path.join(ROOT, "MEASURED_PEAKS.json")

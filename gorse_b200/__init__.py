@@ -273,8 +273,9 @@ class BruteforceIndex:
         check(lib.gorse_b200_index_search_indices(self.h, ptr(q), q.size, k, int(prune0), ptr(idx), ptr(dist), ptr(cnt)))
         return idx, dist, cnt
 
-    def search_range(self, q0, q1, k, prune0=False):
-        idx, dist, cnt = self._out(max(q1 - q0, 0), k)
+    def search_range(self, q0, q1, k, prune0=False, out=None):
+        """out = (idx int32 [nq,k], dist float32 [nq,k], cnt int32 [nq]) to reuse (e.g. pinned) result buffers."""
+        idx, dist, cnt = out if out is not None else self._out(max(q1 - q0, 0), k)
         check(lib.gorse_b200_index_search_range(self.h, q0, q1, k, int(prune0), ptr(idx), ptr(dist), ptr(cnt)))
         return idx, dist, cnt
 

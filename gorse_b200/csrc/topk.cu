@@ -88,6 +88,34 @@ __device__ __forceinline__ void list_insert(float *ld, int32_t *li, int &len, in
     if (len < k) len++;
 }
 
+// the same insertion done by the whole warp: every lane owns list slots lane, lane+32, ...; the position is a ballot count
+// and the shift is one read + one write per owned slot.  All arguments are warp-uniform; len lives in every lane.
+__device__ __forceinline__ void list_insert_warp(float *ld, int32_t *li, int &len, int k, float dv, int32_t iv, int lane)
+{
+    if (len == k && !before(dv, iv, ld[k - 1], li[k - 1])) return;
+    const int n = len;
+    float od[4];
+    int32_t oi[4];
+    int pos = 0;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = lane + 32 * r;
+        const bool has = e < n;
+        od[r] = has ? ld[e] : 0.f;
+        oi[r] = has ? li[e] : 0;
+        pos += __popc(__ballot_sync(0xffffffffu, has && before(od[r], oi[r], dv, iv)));
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = lane + 32 * r;
+        if (e < n && e >= pos && e + 1 < k) { ld[e + 1] = od[r]; li[e + 1] = oi[r]; }
+    }
+    if (lane == 0) { ld[pos] = dv; li[pos] = iv; }
+    if (len < k) len++;
+    __syncwarp();
+}
+
 // Exact scan: one warp per query over vectors [0, N) or over a candidate list.
 //   queries:   nq rows of d floats (q_ptr), or rows of X selected by q_idx when q_ptr == nullptr
 //   self skip: SearchIndex never returns q itself (bruteforce.go:47)
@@ -141,9 +169,10 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
                     float dd = __shfl_sync(0xffffffffu, dv, 4 * s);
                     int64_t vv = __shfl_sync(0xffffffffu, v, 4 * s);
                     int ok = __shfl_sync(0xffffffffu, (int)valid, 4 * s);
-                    if (lane == 0 && ok) {
-                        if (dd != dd) *nan_flag = 1;
-                        else list_insert(ld, li, len, k, dd, (int32_t)vv);
+                    if (ok) {
+                        if (dd != dd) { if (lane == 0) *nan_flag = 1; }
+                        else if (k <= 128) list_insert_warp(ld, li, len, k, dd, (int32_t)vv, lane);
+                        else if (lane == 0) list_insert(ld, li, len, k, dd, (int32_t)vv);
                     }
                 }
                 __syncwarp();
@@ -160,9 +189,10 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
                     float dd = __shfl_sync(0xffffffffu, dv, s);
                     int64_t vv = __shfl_sync(0xffffffffu, v, s);
                     int ok = __shfl_sync(0xffffffffu, (int)valid, s);
-                    if (lane == 0 && ok) {
-                        if (dd != dd) *nan_flag = 1;
-                        else list_insert(ld, li, len, k, dd, (int32_t)vv);
+                    if (ok) {
+                        if (dd != dd) { if (lane == 0) *nan_flag = 1; }
+                        else if (k <= 128) list_insert_warp(ld, li, len, k, dd, (int32_t)vv, lane);
+                        else if (lane == 0) list_insert(ld, li, len, k, dd, (int32_t)vv);
                     }
                 }
                 __syncwarp();

@@ -362,7 +362,18 @@ __global__ void max_kernel(const float *v, int64_t n, float *out)
 }
 
 // ---- stage 2a: prune each row's candidates to the rigorous window and translate to original ids -------------
-// one warp per row; bitonic sort of <= CAP (value, column) pairs by value descending in shared memory
+// One warp per row.  The k-th largest approximate score is found WITHOUT sorting: the scores are mapped to order-preserving
+// 32-bit keys and the key is built bit by bit from the top (32 counting passes over <= CAP values held in shared memory).
+__device__ __forceinline__ uint32_t float_key(float v)
+{
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_float(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
 __global__ void __launch_bounds__(128)
 prune_kernel(const int32_t *cand_col, const float *cand_val, const int32_t *cand_cnt, const float *theta, const float *eps,
              const int32_t *perm, const int64_t *q_idx, int64_t q0, bool self_skip, int64_t nq, int k, int32_t *out_ids /* [nq][CAP] */,
@@ -370,8 +381,8 @@ prune_kernel(const int32_t *cand_col, const float *cand_val, const int32_t *cand
 {
     extern __shared__ uint8_t sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    float *sv = reinterpret_cast<float *>(sm) + (size_t)warp * mma::CAP;
-    int32_t *sc = reinterpret_cast<int32_t *>(reinterpret_cast<float *>(sm) + (size_t)nw * mma::CAP) + (size_t)warp * mma::CAP;
+    uint32_t *sk = reinterpret_cast<uint32_t *>(sm) + (size_t)warp * mma::CAP;                                          // keys
+    int32_t *sc = reinterpret_cast<int32_t *>(reinterpret_cast<uint32_t *>(sm) + (size_t)nw * mma::CAP) + (size_t)warp * mma::CAP;  // ids
     for (int64_t row = (int64_t)blockIdx.x * nw + warp; row < nq; row += (int64_t)gridDim.x * nw) {
         const int raw0 = cand_cnt[2 * row], raw1 = cand_cnt[2 * row + 1];
         const int n0 = min(raw0, mma::HALF_CAP), n1 = min(raw1, mma::HALF_CAP);
@@ -381,51 +392,43 @@ prune_kernel(const int32_t *cand_col, const float *cand_val, const int32_t *cand
         const int64_t self = self_skip ? (q_idx ? q_idx[row] : q0 + row) : -1;
         bool bad = raw0 > mma::HALF_CAP || raw1 > mma::HALF_CAP || !(eps[row] == eps[row]) || !(th == th);
         const int n = n0 + n1;
-        int np2 = 32;
-        while (np2 < n) np2 <<= 1;
-        for (int e = lane; e < np2; e += 32) {
-            float v = -INFINITY;
-            int32_t c = -1;
-            if (e < n) {
-                const int64_t src = row * mma::CAP + (e < n0 ? e : mma::HALF_CAP + (e - n0));
-                c = perm[cand_col[src]];  // original id
-                v = cand_val[src];
-                if (c == self) v = -INFINITY;            // SearchIndex never returns the query itself
-            }
-            sv[e] = v;
+        int have = 0;
+        for (int e = lane; e < n; e += 32) {
+            const int64_t src = row * mma::CAP + (e < n0 ? e : mma::HALF_CAP + (e - n0));
+            const int32_t c = perm[cand_col[src]];  // original id
+            const float v = cand_val[src];
+            const bool keep = c != self && v == v;   // SearchIndex never returns the query itself
+            sk[e] = keep ? float_key(v) : 0u;
             sc[e] = c;
+            have += keep;
         }
+        for (int o = 16; o; o >>= 1) have += __shfl_xor_sync(0xffffffffu, have, o);
         __syncwarp();
-        for (int size = 2; size <= np2; size <<= 1)
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int e = lane; e < np2 / 2; e += 32) {
-                    const int lo = 2 * e - (e & (stride - 1)), hi = lo + stride;
-                    const bool desc = (lo & size) == 0;
-                    const float a = sv[lo], b = sv[hi];
-                    if (desc ? a < b : a > b) { sv[lo] = b; sv[hi] = a; const int32_t t = sc[lo]; sc[lo] = sc[hi]; sc[hi] = t; }
-                }
-                __syncwarp();
-            }
-        // validity: at least k candidates clear theta + 2 eps, i.e. the k-th best approximate score is known exactly
-        const float two_eps = 2.f * eps[row];
+        if (have < k) bad = true;
         int w = 0;
         if (!bad) {
-            const int have = n - (self >= 0 ? 1 : 0);  // upper bound; -inf entries sort last anyway
-            if (have < k || !(sv[k - 1] >= th + two_eps)) bad = true;
-        }
-        if (!bad) {
-            const float lim = sv[k - 1] - two_eps;
-            // window = prefix of the sorted list with value >= lim
-            int cntw = 0;
-            for (int e0 = 0; e0 < np2; e0 += 32) {
-                const int e = e0 + lane;
-                const bool in = e < n && sv[e] >= lim && sc[e] >= 0 && sv[e] > -INFINITY;
-                const unsigned mk = __ballot_sync(0xffffffffu, in);
-                if (in) oi[cntw + __popc(mk & ((1u << lane) - 1))] = sc[e];
-                cntw += __popc(mk);
-                if (mk != 0xffffffffu) break;
+            uint32_t t = 0;
+            for (int bit = 31; bit >= 0; bit--) {
+                const uint32_t candk = t | (1u << bit);
+                int cnt = 0;
+                for (int e = lane; e < n; e += 32) cnt += sk[e] >= candk;
+                for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                if (cnt >= k) t = candk;
             }
-            w = cntw;
+            const float kth = key_float(t);            // the k-th largest approximate score
+            const float two_eps = 2.f * eps[row];
+            // validity: at least k candidates clear theta + 2 eps, i.e. the k-th best approximate score is known exactly
+            if (!(kth >= th + two_eps)) bad = true;
+            else {
+                const uint32_t lim = float_key(kth - two_eps);
+                for (int e0 = 0; e0 < n; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool in = e < n && sk[e] >= lim && sk[e] != 0u;
+                    const unsigned mk = __ballot_sync(0xffffffffu, in);
+                    if (in) oi[w + __popc(mk & ((1u << lane) - 1))] = sc[e];
+                    w += __popc(mk);
+                }
+            }
         }
         if (lane == 0) {
             out_cnt[row] = bad ? 0 : w;
