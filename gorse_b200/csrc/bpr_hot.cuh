@@ -1,4 +1,4 @@
-// bpr_hot.cuh -- the "hot owner" half of a BPR epoch.
+// bpr_hot.cuh -- the hot-item half of a BPR epoch: queue, counting sort, capped-concurrency apply.
 //
 // Why it exists: with a popularity head (Zipf(1.0): the top item is the positive of ~7 % of all
 // triples) free-running Hogwild on a GPU has two problems the reference's 8-128 goroutines do not have:

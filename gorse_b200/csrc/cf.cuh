@@ -42,7 +42,7 @@ struct gorse_b200_cf {
     gb::DevBuf<int32_t> user_items, item_users, active;
     gb::DevBuf<gb::UserMeta> user_meta;
     bool all_active = false;  // every user of the shard has feedback: active[k] == u_lo + k
-    // hot items (BPR): the head of the popularity distribution, trained by owner CTAs (bpr_hot.cuh)
+    // hot items (BPR): the head of the popularity distribution, applied with capped per-row concurrency (bpr_hot.cuh)
     int32_t n_hot = 0, hot_pad = 0;
     gb::DevBuf<int32_t> hot_items, hot_slot;   // slot -> item (decreasing mass), item -> slot or -1
     gb::DevBuf<float> hot;                     // striped side table the hot rows live in during an epoch
