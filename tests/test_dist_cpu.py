@@ -32,18 +32,18 @@ dist.all_reduce(t, op=dist.ReduceOp.MAX)
 assert t.item() == world
 dist.barrier()
 dist.destroy_process_group()
-print("rank", rank, "ok")
+open(os.path.join(%r, f"ok_{rank}"), "w").write("ok")
 '''
 
 
 def test_gloo_world2_plumbing(tmp_path):
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % ROOT)
+    script.write_text(WORKER % (ROOT, str(tmp_path)))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert (tmp_path / "ok_0").exists() and (tmp_path / "ok_1").exists()
 
 
 def test_reference_arm_prints_contract_line():
