@@ -423,7 +423,18 @@ __global__ void bpr_sample_kernel(BprView v, uint64_t base, int64_t first, int64
     }
 }
 
-// distributed item-factor exchange: Q <- Q - Q0 (local delta); all-reduce; Q <- Q0 + sum; Q0 <- Q
+// ---- distributed item-factor exchange ------------------------------------------------------------
+// Each rank runs its share of the epoch against its replica Q_r of the item table (started from the common Q0);
+// then  Q <- Q0 + s_i * sum_r (Q_r - Q0)  row by row.  Plainly summing the deltas (s = 1) is what one replica
+// would have done only while every row moves a small fraction of the way to its local fixed point per epoch.  A
+// row that is updated n times moves the fraction a = 1 - (1 - lr*kappa)^n of that way (kappa = reg + curvature of
+// the logistic loss), so W ranks summed overshoot by the factor W*a: for the head of the popularity distribution
+// a ~ 1 and the sum diverges within a few epochs once W > 2 (tools/dist_rule_sim.py reproduces it with the CPU
+// oracle).  Composing the W relaxations one after the other, as the single replica does, gives the total fraction
+// 1 - prod_r (1 - a_r); scaling the summed delta by  s_i = (1 - prod_r (1 - a_ir)) / sum_r a_ir  keeps the plain sum
+// for rarely-updated rows (s -> 1) and turns into the average of the replicas for saturated ones (s -> 1/W).
+// n_ir is the EXPECTED update count (item_rate * local steps), kappa = reg + 2*E|p|^2/d (isotropic estimate of
+// 0.25*lambda_max(E[p p^T]) with a safety factor of 8 for anisotropy), E|p|^2 sampled from the local user shard.
 __global__ void q_delta_kernel(float4 *q, const float4 *q0, int64_t n4)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
@@ -432,25 +443,62 @@ __global__ void q_delta_kernel(float4 *q, const float4 *q0, int64_t n4)
         q[i] = make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
     }
 }
-__global__ void q_apply_kernel(float4 *q, float4 *q0, int64_t n4)
-{
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n4; i += st) {
-        float4 a = q[i], b = q0[i];
-        float4 r = make_float4(b.x + a.x, b.y + a.y, b.z + a.z, b.w + a.w);
-        q[i] = r;
-        q0[i] = r;
-    }
-}
 __global__ void q_delta_scalar_kernel(float *q, const float *q0, int64_t n)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += st) q[i] = q[i] - q0[i];
 }
-__global__ void q_apply_scalar_kernel(float *q, float *q0, int64_t n)
+// one warp per sampled row: psq[0] += |p|^2, psq[1] += 1
+__global__ void p_norm_sample_kernel(const float *P, int64_t n_rows, int d, int64_t stride, int64_t n_sample, float *psq)
+{
+    const int lane = threadIdx.x & 31;
+    int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    float acc = 0.f, cnt = 0.f;
+    for (; w < n_sample; w += nw) {
+        const int64_t r = w * stride;
+        if (r >= n_rows) break;
+        const float *row = P + r * d;
+        for (int f = lane; f < d; f += 32) { float x = row[f]; acc += x * x; }
+        cnt += 1.f;
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0 && cnt > 0.f) { atomicAdd(&psq[0], acc); atomicAdd(&psq[1], cnt); }
+}
+// xchg = [ a (n_items) | L (n_items) | psq (2) ]: a_i = 1 - (1 - lr*kappa)^{n_i}, L_i = n_i * log(1 - lr*kappa)
+__global__ void xchg_prepare_kernel(const float *rate, int32_t n_items, float n_local_steps, float lr, float reg, int d, float *xchg)
+{
+    const float *psq = xchg + 2 * (int64_t)n_items;
+    const float p2 = psq[1] > 0.f ? psq[0] / psq[1] : 0.f;
+    const float kappa = reg + 2.0f * p2 / (float)d;
+    const float l1 = log1pf(-fminf(fmaxf(lr * kappa, 0.f), 0.5f));
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i < n_items; i += gridDim.x * blockDim.x) {
+        const float L = n_local_steps * rate[i] * l1;
+        xchg[i] = -expm1f(L);
+        xchg[n_items + i] = L;
+    }
+}
+__device__ __forceinline__ float xchg_scale(const float *xchg, int32_t n_items, int32_t i)
+{
+    const float a = xchg[i], L = xchg[n_items + i];
+    return a > 1e-12f ? fminf(1.0f, -expm1f(L) / a) : 1.0f;
+}
+__global__ void q_apply_kernel(float4 *q, float4 *q0, int64_t n4, int d4, const float *xchg, int32_t n_items)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
-    for (; i < n; i += st) { float r = q0[i] + q[i]; q[i] = r; q0[i] = r; }
+    for (; i < n4; i += st) {
+        const float s = xchg_scale(xchg, n_items, (int32_t)(i / d4));
+        float4 a = q[i], b = q0[i];
+        float4 r = make_float4(b.x + s * a.x, b.y + s * a.y, b.z + s * a.z, b.w + s * a.w);
+        q[i] = r;
+        q0[i] = r;
+    }
+}
+__global__ void q_apply_scalar_kernel(float *q, float *q0, int64_t n, int d, const float *xchg, int32_t n_items)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) { float r = q0[i] + xchg_scale(xchg, n_items, (int32_t)(i / d)) * q[i]; q[i] = r; q0[i] = r; }
 }
 
 static BprView make_view(gorse_b200_cf *cf)
@@ -692,10 +740,22 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
         if (n % 4 == 0) q_delta_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (const float4 *)cf->Q0.p, n / 4);
         else q_delta_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n);
         GB_LAUNCHED(c);
+        // per-row damping inputs (see the comment above q_delta_kernel)
+        float *psq = cf->xchg.p + 2 * (int64_t)cf->n_items;
+        GB_CUDA(cudaMemsetAsync(psq, 0, 4 * sizeof(float), c->stream));
+        const int64_t n_rows = cf->u_hi - cf->u_lo;
+        if (n_rows > 0 && s1 > s0) {
+            const int64_t n_sample = std::min<int64_t>(n_rows, 65536), stride = std::max<int64_t>(1, n_rows / n_sample);
+            p_norm_sample_kernel<<<(int)std::min<int64_t>(div_up(n_sample * 32, 256), c->sm_count * 8), 256, 0, c->stream>>>(cf->P.p, n_rows, cf->d, stride, n_sample, psq);
+            GB_LAUNCHED(c);
+        }
+        xchg_prepare_kernel<<<(int)std::min<int64_t>(div_up(cf->n_items, 256), c->sm_count * 8), 256, 0, c->stream>>>(cf->item_rate.p, cf->n_items, (float)(s1 - s0), lr, reg, cf->d, cf->xchg.p);
+        GB_LAUNCHED(c);
         GB_NCCL_API(nc);
         GB_NCCL(nc, AllReduce(cf->Q.p, cf->Q.p, (size_t)n, ncclFloat32, ncclSum, c->comm, c->stream));
-        if (n % 4 == 0) q_apply_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (float4 *)cf->Q0.p, n / 4);
-        else q_apply_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n);
+        GB_NCCL(nc, AllReduce(cf->xchg.p, cf->xchg.p, (size_t)2 * cf->n_items, ncclFloat32, ncclSum, c->comm, c->stream));
+        if (n % 4 == 0) q_apply_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (float4 *)cf->Q0.p, n / 4, cf->d / 4, cf->xchg.p, cf->n_items);
+        else q_apply_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n, cf->d, cf->xchg.p, cf->n_items);
         GB_LAUNCHED(c);
     }
     return GORSE_B200_OK;

@@ -153,6 +153,7 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     // hot items: an item drawn as the positive of more than ~0.02% of an epoch's triples would serialise on one
     // L2 atomic unit; P(i) is proportional to sum_{u in R_i} 1/|R_u| (user uniform, then item uniform in the row)
     std::vector<int32_t> hot_items, hot_slot;
+    std::vector<float> item_rate;
     {
         std::vector<double> mass((size_t)n_items, 0.0);
         for (int32_t u = cf->u_lo; u < cf->u_hi; u++) {
@@ -173,11 +174,20 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
         }
         cf->n_hot = (int32_t)hot_items.size();
         cf->hot_pad = std::max(64, (cf->n_hot + 63) / 64 * 64);
+        if (ctx->world > 1) {
+            // expected updates of item i per local step: P(i is the positive) + P(i is the negative ~ uniform)
+            item_rate.resize((size_t)n_items);
+            for (int32_t i = 0; i < n_items; i++) item_rate[(size_t)i] = (float)(mass[(size_t)i] / total + 1.0 / (double)n_items);
+        }
     }
     int64_t n_local = cf->u_hi - cf->u_lo;
     if ((st = cf->P.alloc((size_t)n_local * n_factors)) != 0) return fail(st);
     if ((st = cf->Q.alloc((size_t)n_items * n_factors)) != 0) return fail(st);
-    if (ctx->world > 1 && (st = cf->Q0.alloc((size_t)n_items * n_factors)) != 0) return fail(st);
+    if (ctx->world > 1) {
+        if ((st = cf->Q0.alloc((size_t)n_items * n_factors)) != 0) return fail(st);
+        if ((st = cf->item_rate.alloc((size_t)n_items)) != 0) return fail(st);
+        if ((st = cf->xchg.alloc((size_t)2 * n_items + 4)) != 0) return fail(st);
+    }
     if ((st = cf->user_off.alloc((size_t)n_users + 1)) != 0) return fail(st);
     if ((st = cf->user_items.alloc((size_t)cf->n_feedback)) != 0) return fail(st);
     if ((st = cf->active.alloc(active.size())) != 0) return fail(st);
@@ -197,6 +207,7 @@ int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_ite
     if ((st = up(cf->user_items.p, sorted.data(), sizeof(int32_t) * (size_t)cf->n_feedback)) != 0) return fail(st);
     if ((st = up(cf->active.p, active.data(), sizeof(int32_t) * active.size())) != 0) return fail(st);
     if ((st = up(cf->user_meta.p, meta.data(), sizeof(UserMeta) * meta.size())) != 0) return fail(st);
+    if ((st = up(cf->item_rate.p, item_rate.data(), sizeof(float) * item_rate.size())) != 0) return fail(st);
     if (cf->n_hot) {
         if ((st = up(cf->hot_items.p, hot_items.data(), sizeof(int32_t) * hot_items.size())) != 0) return fail(st);
         if ((st = up(cf->hot_slot.p, hot_slot.data(), sizeof(int32_t) * hot_slot.size())) != 0) return fail(st);
@@ -223,7 +234,7 @@ int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
     if (!cf) return GORSE_B200_OK;
     ScopedDevice sd(cf->ctx->device);
     cudaStreamSynchronize(cf->ctx->stream);
-    cf->P.free(); cf->Q.free(); cf->Q0.free();
+    cf->P.free(); cf->Q.free(); cf->Q0.free(); cf->item_rate.free(); cf->xchg.free();
     cf->user_off.free(); cf->item_off.free();
     cf->user_items.free(); cf->item_users.free(); cf->active.free(); cf->user_meta.free();
     cf->hot_items.free(); cf->hot_slot.free(); cf->hot.free(); cf->hotq.free(); cf->hot_sorted.free(); cf->hot_ctr.free();

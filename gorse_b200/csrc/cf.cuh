@@ -38,6 +38,8 @@ struct gorse_b200_cf {
     int32_t n_active = 0;
     bool has_item_csr = false;
     gb::DevBuf<float> P, Q, Q0;
+    // multi-rank item exchange (bpr.cu): expected updates of item i per local BPR step, and the [a | L | psq] buffer
+    gb::DevBuf<float> item_rate, xchg;
     gb::DevBuf<int64_t> user_off, item_off;
     gb::DevBuf<int32_t> user_items, item_users, active;
     gb::DevBuf<gb::UserMeta> user_meta;
