@@ -206,6 +206,137 @@ als_rows_kernel(float *X, const float *Y, int d, int32_t x_lo, int32_t y_lo, con
     }
 }
 
+// ---- short rows, lane-group form (d % 32 == 0, d <= 128) ---------------------------------------------------
+// A group of G lanes (8 or 32) owns one row; 32/G rows share a warp.  With h_f = sum_t y_tf, c_f = (1-w) sum_t y_tf^2
+// and g = S x kept CURRENT (g += delta * S[f,:] after every coordinate), the reference's step (model.go:666-680) is
+//     x_f <- ( h_f - (1-w) * sum_t pred_t y_tf + x_f * (c_f + w S_ff) - w * g_f ) / (c_f + w S_ff + reg)
+// (a = h_f - (1-w) z_f + x_f c_f,  b = w (g_f - S_ff x_f)): the only reduction on the strictly sequential f chain is
+// z_f over the row's entries (log2 G shuffles); h, c and the reciprocal denominators are computed up front, lane
+// parallel, and the S-part of b needs no reduction at all.  Lane j of the group owns the factors k = i*G + j
+// (i < KPL = d/G) of x, g, h, c in registers and the entries t = j + e*G (e < E) of pred; the gathered rows sit in
+// shared memory as [t][d+1] (conflict-free both along a row and down a column) next to one copy of S per CTA.
+// Differences from the reference are reassociation (lane-parallel sums, incremental g) and one reciprocal-multiply
+// instead of a divide: observed ~1e-6 relative, budget 1e-4.
+template <int G>
+__device__ __forceinline__ float group_sum(float v)
+{
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int G, int E, int KPL>
+__global__ void __launch_bounds__(256)
+als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_t *idx, const float *S, float reg, float w,
+                      const int32_t *row_ids, int32_t n_rows)
+{
+    constexpr int D = G * KPL, DP = D + 1, NG = 32 / G, D4 = D / 4;
+    extern __shared__ float smem[];
+    float *Ss = smem;                                   // [D][D]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int grp = lane / G, j = lane % G;
+    float *ys = smem + D * D + (size_t)(wid * NG + grp) * (G * E * DP);
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) Ss[e] = S[e];
+    __syncthreads();
+    const float omw = 1.0f - w;
+    const int32_t stride = gridDim.x * nw * NG;
+    for (int32_t base = (blockIdx.x * nw + wid) * NG; base < n_rows; base += stride) {   // warp-uniform trip count
+        const int32_t slot = base + grp;
+        const bool act = slot < n_rows;
+        int32_t r = 0;
+        int n = 0;
+        int64_t o = 0;
+        if (act) { r = row_ids[slot]; o = off[r]; n = (int)(off[r + 1] - o); }
+        // stage the gathered rows: the group's lanes walk the n*D/4 float4 pieces
+#pragma unroll 4
+        for (int c = j; c < n * D4; c += G) {
+            const int t = c / D4, q = c - t * D4;
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx[o + t] * D) + q);
+            float *dst = ys + t * DP + 4 * q;
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        }
+        float x[KPL], g[KPL], h[KPL], cw[KPL], inv[KPL], pred[E];
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            x[i] = act ? X[(int64_t)r * D + i * G + j] : 0.f;
+            g[i] = 0.f; h[i] = 0.f; cw[i] = 0.f;
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) pred[e] = 0.f;
+        __syncwarp();
+        // pred_t = x . y_t (:661-663), h, c in one pass over the staged rows
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+#pragma unroll 1
+            for (int tt = 0; tt < G; tt++) {
+                const int t = e * G + tt;
+                if (t >= nmax) break;                    // warp-uniform
+                float part = 0.f;
+                if (t < n) {
+#pragma unroll
+                    for (int i = 0; i < KPL; i++) {
+                        const float y = ys[t * DP + i * G + j];
+                        part = fmaf(x[i], y, part);
+                        h[i] += y;
+                        cw[i] = fmaf(y, y, cw[i]);
+                    }
+                }
+                part = group_sum<G>(part);
+                if (tt == j) pred[e] = part;
+            }
+        }
+        // g = S x (S symmetric: row m is column m), cw = (1-w) c + w S_kk, inv = 1 / (cw + reg)
+#pragma unroll
+        for (int mi = 0; mi < KPL; mi++) {
+#pragma unroll 1
+            for (int mj = 0; mj < G; mj++) {
+                const float xm = __shfl_sync(0xffffffffu, x[mi], mj, G);
+                const float *srow = Ss + (mi * G + mj) * D + j;
+#pragma unroll
+                for (int i = 0; i < KPL; i++) g[i] = fmaf(xm, srow[i * G], g[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            const int k = i * G + j;
+            cw[i] = omw * cw[i] + w * Ss[k * D + k];
+            inv[i] = 1.0f / (cw[i] + reg);
+        }
+        // the sequential sweep over f = fi*G + jo
+#pragma unroll
+        for (int fi = 0; fi < KPL; fi++) {
+#pragma unroll 1
+            for (int jo = 0; jo < G; jo++) {
+                const int f = fi * G + jo;
+                float ye[E];
+                float part = 0.f;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const int t = j + e * G;
+                    ye[e] = t < n ? ys[t * DP + f] : 0.f;
+                    part = fmaf(pred[e], ye[e], part);
+                }
+                const float z = group_sum<G>(part);
+                const float num = (h[fi] - omw * z) + (x[fi] * cw[fi] - w * g[fi]);
+                const float xn = num * inv[fi];
+                const float dl = __shfl_sync(0xffffffffu, xn - x[fi], jo, G);
+                if (j == jo) x[fi] = xn;
+#pragma unroll
+                for (int e = 0; e < E; e++) pred[e] = fmaf(dl, ye[e], pred[e]);
+                const float *srow = Ss + f * D + j;
+#pragma unroll
+                for (int i = 0; i < KPL; i++) g[i] = fmaf(dl, srow[i * G], g[i]);
+            }
+        }
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < KPL; i++) X[(int64_t)r * D + i * G + j] = x[i];
+        }
+        __syncwarp();   // the next row's staging must not overtake this row's column reads
+    }
+}
+
 // ---- Gram form for rows too long to stage ---------------------------------------------------
 // eALS over f for one row is exactly one Gauss-Seidel sweep on  A x = h  with
 //     A = (1-w) * G + w * S + reg * I,   G = sum_{t in R} y_t y_t^T,   h = sum_{t in R} y_t
@@ -336,26 +467,33 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
     return GORSE_B200_OK;
 }
 
-// rows bucketed by length so that each launch has a shared-memory budget that fits its rows:
-//   class 0: n*(d+1) <= 3072 floats  (12 KB/warp, 4 CTAs/SM)
-//   class 1: n*(d+1) <= 12288 floats (48 KB/warp, 1 CTA/SM)
-//   class 2: longer rows, gathered from L2 (no staging)
-static const int kStageFloats[3] = {3072, 12288, 0};
+// rows bucketed by length, one launch per class:
+//   lane-group form (d % 32 == 0, d <= 128; als_rows_group_kernel):  n <= 8 | n <= 32 | n <= 96 | longer -> Gram form
+//   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp) | - |
+//   longer -> Gram form when d <= 128, else gathered from L2 without staging
+static const int kStageFloats[2] = {3072, 12288};
+static const int kGroupRows[3] = {8, 32, 96};
+#define GB_ALS_LONG 3   // index of the long-row class
+
+static bool als_grouped(const gorse_b200_cf *cf) { return cf->d % 32 == 0 && cf->d <= 128; }
 
 static int32_t prepare_als(gorse_b200_cf *cf)
 {
     if (cf->als_ready) return GORSE_B200_OK;
     const int dp = cf->d + 1;
+    const bool grouped = als_grouped(cf);
     for (int side = 0; side < 2; side++) {
         const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
         int32_t rows = side == 0 ? cf->n_users : cf->n_items;
-        std::vector<int32_t> cls[3];
+        std::vector<int32_t> cls[4];
         for (int32_t r = 0; r < rows; r++) {
             int64_t n = off[(size_t)r + 1] - off[r];
-            int k = n * dp <= kStageFloats[0] ? 0 : n * dp <= kStageFloats[1] ? 1 : 2;
+            int k;
+            if (grouped) k = n <= kGroupRows[0] ? 0 : n <= kGroupRows[1] ? 1 : n <= kGroupRows[2] ? 2 : GB_ALS_LONG;
+            else k = n * dp <= kStageFloats[0] ? 0 : n * dp <= kStageFloats[1] ? 1 : GB_ALS_LONG;
             cls[k].push_back(r);
         }
-        for (int k = 0; k < 3; k++) {
+        for (int k = 0; k < 4; k++) {
             // longest rows first inside a class: better tail behaviour
             std::stable_sort(cls[k].begin(), cls[k].end(), [&](int32_t a, int32_t b) {
                 return off[(size_t)a + 1] - off[a] > off[(size_t)b + 1] - off[b];
@@ -366,12 +504,12 @@ static int32_t prepare_als(gorse_b200_cf *cf)
                 GB_CUDA(cudaMemcpy(cf->als_rows[side][k].p, cls[k].data(), sizeof(int32_t) * cls[k].size(), cudaMemcpyHostToDevice));
         }
     }
-    // long rows (class 2) take the Gram form when d <= 128: cut them into chunks
+    // long rows take the Gram form when d <= 128: cut them into chunks
     for (int side = 0; side < 2 && cf->d <= 128; side++) {
         const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
-        std::vector<int32_t> rows((size_t)cf->als_rows_n[side][2]);
+        std::vector<int32_t> rows((size_t)cf->als_rows_n[side][GB_ALS_LONG]);
         if (rows.empty()) continue;
-        GB_CUDA(cudaMemcpy(rows.data(), cf->als_rows[side][2].p, sizeof(int32_t) * rows.size(), cudaMemcpyDeviceToHost));
+        GB_CUDA(cudaMemcpy(rows.data(), cf->als_rows[side][GB_ALS_LONG].p, sizeof(int32_t) * rows.size(), cudaMemcpyDeviceToHost));
         std::vector<int32_t> chunk_row, chunk_len, row_chunk0;
         std::vector<int64_t> chunk_begin;
         for (size_t i = 0; i < rows.size(); i++) {
@@ -405,14 +543,46 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     return GORSE_B200_OK;
 }
 
+template <int G, int E, int KPL>
+static int32_t launch_group(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
+                            const int32_t *rows, int32_t n_rows)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    constexpr int D = G * KPL, DP = D + 1;
+    const size_t s_bytes = sizeof(float) * D * D, per_warp = sizeof(float) * 32 * E * DP;
+    const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024 - s_bytes) / per_warp));
+    const size_t sm = s_bytes + warps * per_warp;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (32 * warps), (227 * 1024) / (sm + 1024)));
+    const int groups_per_cta = warps * (32 / G);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_rows + groups_per_cta - 1) / groups_per_cta, (int64_t)c->sm_count * ctas_per_sm));
+    GB_CUDA(cudaFuncSetAttribute(als_rows_group_kernel<G, E, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    als_rows_group_kernel<G, E, KPL><<<grid, 32 * warps, sm, c->stream>>>(X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows);
+    GB_LAUNCHED(c);
+    return GORSE_B200_OK;
+}
+
+template <int G, int E>
+static int32_t launch_group_d(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
+                              const int32_t *rows, int32_t n_rows)
+{
+    switch (cf->d / 32) {
+        case 1: return launch_group<G, E, 32 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+        case 2: return launch_group<G, E, 64 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+        case 3: return launch_group<G, E, 96 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+        default: return launch_group<G, E, 128 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+    }
+}
+
 static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, const int64_t *off, const int32_t *idx,
                         float reg, float w, float *pred_scratch)
 {
     gorse_b200_ctx *c = cf->ctx;
-    for (int k = 0; k < 3; k++) {
+    const bool grouped = als_grouped(cf);
+    for (int k = 0; k < 4; k++) {
         int32_t n_rows = cf->als_rows_n[side][k];
         if (n_rows == 0) continue;
-        if (k == 2 && cf->als_n_chunks[side] > 0) {
+        const int32_t *rows = cf->als_rows[side][k].p;
+        if (k == GB_ALS_LONG && cf->als_n_chunks[side] > 0) {
             const int d = cf->d, T = d <= 16 ? 1 : d <= 32 ? 2 : d <= 64 ? 4 : 8;
             const size_t gsm = sizeof(float) * 16 * 16 * T;
             const int nc = cf->als_n_chunks[side];
@@ -424,15 +594,22 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             }
             GB_LAUNCHED(c);
             const size_t ssm = sizeof(float) * ((size_t)d * (d + 1) + 2 * d);
-            als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, cf->als_rows[side][2].p, cf->als_row_chunk0[side].p, cf->als_partial.p);
+            als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, rows, cf->als_row_chunk0[side].p, cf->als_partial.p);
             GB_LAUNCHED(c);
             continue;
         }
-        size_t sm = sizeof(float) * GB_ALS_WARPS * (size_t)(cf->d + kStageFloats[k]);
+        if (grouped && k != GB_ALS_LONG) {
+            if (k == 0) GB_TRY((launch_group_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else if (k == 1) GB_TRY((launch_group_d<32, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else GB_TRY((launch_group_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            continue;
+        }
+        // one warp per row; the long class without a Gram form (d > 128) gathers from L2 without staging
+        const int stage = k == GB_ALS_LONG ? 0 : kStageFloats[k];
+        size_t sm = sizeof(float) * GB_ALS_WARPS * (size_t)(cf->d + stage);
         int ctas_per_sm = k == 0 ? 4 : 1;
-        int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + GB_ALS_WARPS - 1) / GB_ALS_WARPS, (int64_t)c->sm_count * ctas_per_sm * (k == 2 ? 8 : 1)));
-        als_rows_kernel<<<grid, 32 * GB_ALS_WARPS, sm, c->stream>>>(X, Y, cf->d, 0, 0, off, idx, cf->gram.p, reg, w,
-                                                                  cf->als_rows[side][k].p, n_rows, kStageFloats[k], pred_scratch);
+        int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + GB_ALS_WARPS - 1) / GB_ALS_WARPS, (int64_t)c->sm_count * ctas_per_sm * (k == GB_ALS_LONG ? 8 : 1)));
+        als_rows_kernel<<<grid, 32 * GB_ALS_WARPS, sm, c->stream>>>(X, Y, cf->d, 0, 0, off, idx, cf->gram.p, reg, w, rows, n_rows, stage, pred_scratch);
         GB_LAUNCHED(c);
     }
     return GORSE_B200_OK;

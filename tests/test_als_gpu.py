@@ -21,7 +21,8 @@ def rel_err(a, b):
 
 
 @pytest.mark.parametrize("d,U,I,R", [(16, 400, 150, 6000), (8, 200, 80, 2000), (64, 300, 100, 5000),
-                                      (128, 200, 60, 3000), (10, 150, 50, 1500), (160, 60, 40, 900)])
+                                      (128, 200, 60, 3000), (10, 150, 50, 1500), (160, 60, 40, 900),
+                                      (96, 250, 70, 4000), (32, 500, 30, 9000), (128, 2000, 40, 9000)])
 def test_one_epoch_matches_oracle(gb, orc, ctx, d, U, I, R):
     from gorse_b200 import synth
 
