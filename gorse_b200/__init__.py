@@ -279,8 +279,44 @@ class BruteforceIndex:
         check(lib.gorse_b200_index_search_range(self.h, q0, q1, k, int(prune0), ptr(idx), ptr(dist), ptr(cnt)))
         return idx, dist, cnt
 
+    def query_similar(self, q0, q1, n, score_scale=1.0):
+        """logics.QueryItemToItem / QueryUserToUser for stored vectors [q0, q1) (logics/item_to_item.go:50-86):
+        (ids int32 [nq,n] padded with -1, scores float64 [nq,n], cnt int32 [nq])."""
+        nq = max(q1 - q0, 0)
+        ids, sc, cnt = np.full((nq, n), -1, np.int32), np.zeros((nq, n), np.float64), np.zeros(nq, np.int32)
+        check(lib.gorse_b200_index_query_similar(self.h, q0, q1, n, float(score_scale), ptr(ids), ptr(sc), ptr(cnt)))
+        return ids, sc, cnt
+
     def __enter__(self):
         return self
 
     def __exit__(self, *a):
         self.close()
+
+
+# ---- logics: similarity vectors and scores (host functions; SURVEY 8a row J) ---------------------------------
+def bf16_truncate(a):
+    """bfloats.FromFloat32 + ToFloat32 (common/bfloats/bfloats.go:23-37): how the reference stores dense embeddings."""
+    a = np.ascontiguousarray(a, np.float32)
+    out = np.empty_like(a)
+    check(lib.gorse_b200_bf16_truncate(ptr(a), a.size, ptr(out)))
+    return out
+
+
+def sparse_vector(ids, idf, offset=0):
+    """appendSparseVector (logics/vector_writer.go:200-209) -> (indices uint32, values float32)."""
+    ids, idf = np.ascontiguousarray(ids, np.int32), np.ascontiguousarray(idf, np.float32)
+    ind, val = np.zeros(max(len(ids), 1), np.uint32), np.zeros(max(len(ids), 1), np.float32)
+    m = C.c_int32(0)
+    check(lib.gorse_b200_sparse_vector(ptr(ids), len(ids), ptr(idf), len(idf), int(offset), ptr(ind), ptr(val), C.byref(m)))
+    return ind[:m.value], val[:m.value]
+
+
+def similar_scores(metric, score_scale, self_id, n, nbr_ids, nbr_dist):
+    """QueryItemToItem post-processing (logics/item_to_item.go:63-85) of one result row of BruteforceIndex."""
+    nbr_ids, nbr_dist = np.ascontiguousarray(nbr_ids, np.int32), np.ascontiguousarray(nbr_dist, np.float32)
+    ids, sc = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    m = C.c_int32(0)
+    check(lib.gorse_b200_similar_scores(int(metric), float(score_scale), int(self_id), int(n), ptr(nbr_ids), ptr(nbr_dist),
+                                        len(nbr_ids), ptr(ids), ptr(sc), C.byref(m)))
+    return ids[:m.value], sc[:m.value]

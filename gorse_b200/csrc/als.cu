@@ -225,7 +225,7 @@ __device__ __forceinline__ float group_sum(float v)
     return v;
 }
 
-template <int G, int E, int KPL>
+template <int G, int E, int KPL, int B>
 __global__ void __launch_bounds__(256)
 als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_t *idx, const float *S, float reg, float w,
                       const int32_t *row_ids, int32_t n_rows)
@@ -303,30 +303,67 @@ als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_
             cw[i] = omw * cw[i] + w * Ss[k * D + k];
             inv[i] = 1.0f / (cw[i] + reg);
         }
-        // the sequential sweep over f = fi*G + jo
+        // the sequential sweep over f = fi*G + jo, B coordinates at a time: the B reductions z_b = sum_t pred_t y_tb and
+        // the B(B-1)/2 in-block products M_ab = sum_t y_ta y_tb run as ONE interleaved butterfly, then the coordinates
+        // are resolved in order with z_b += delta_a * M_ab  (pred_t moves by delta_a * y_ta, hence z_b by delta_a * M_ab):
+        // same arithmetic as one coordinate at a time up to rounding, a B-fold shorter dependent chain of shuffles.
+        constexpr int NV = B + B * (B - 1) / 2;
 #pragma unroll
         for (int fi = 0; fi < KPL; fi++) {
 #pragma unroll 1
-            for (int jo = 0; jo < G; jo++) {
-                const int f = fi * G + jo;
-                float ye[E];
-                float part = 0.f;
+            for (int jb = 0; jb < G / B; jb++) {
+                const int f0 = fi * G + jb * B;
+                float ye[E][B], red[NV], dls[B];
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const int t = j + e * G;
-                    ye[e] = t < n ? ys[t * DP + f] : 0.f;
-                    part = fmaf(pred[e], ye[e], part);
+#pragma unroll
+                    for (int a = 0; a < B; a++) ye[e][a] = t < n ? ys[t * DP + f0 + a] : 0.f;
                 }
-                const float z = group_sum<G>(part);
-                const float num = (h[fi] - omw * z) + (x[fi] * cw[fi] - w * g[fi]);
-                const float xn = num * inv[fi];
-                const float dl = __shfl_sync(0xffffffffu, xn - x[fi], jo, G);
-                if (j == jo) x[fi] = xn;
 #pragma unroll
-                for (int e = 0; e < E; e++) pred[e] = fmaf(dl, ye[e], pred[e]);
-                const float *srow = Ss + f * D + j;
+                for (int a = 0; a < B; a++) {
+                    float v = 0.f;
 #pragma unroll
-                for (int i = 0; i < KPL; i++) g[i] = fmaf(dl, srow[i * G], g[i]);
+                    for (int e = 0; e < E; e++) v = fmaf(pred[e], ye[e][a], v);
+                    red[a] = v;
+                }
+                {
+                    int q = B;
+#pragma unroll
+                    for (int a = 0; a < B; a++)
+#pragma unroll
+                        for (int b2 = a + 1; b2 < B; b2++) {
+                            float v = 0.f;
+#pragma unroll
+                            for (int e = 0; e < E; e++) v = fmaf(ye[e][a], ye[e][b2], v);
+                            red[q++] = v;
+                        }
+                }
+#pragma unroll
+                for (int o = G / 2; o; o >>= 1)
+#pragma unroll
+                    for (int v = 0; v < NV; v++) red[v] += __shfl_xor_sync(0xffffffffu, red[v], o);
+                {
+                    int q = B;
+#pragma unroll
+                    for (int a = 0; a < B; a++) {
+                        const int jo = jb * B + a;
+                        const float num = (h[fi] - omw * red[a]) + (x[fi] * cw[fi] - w * g[fi]);
+                        const float xn = num * inv[fi];
+                        const float dl = __shfl_sync(0xffffffffu, xn - x[fi], jo, G);
+                        if (j == jo) x[fi] = xn;
+                        dls[a] = dl;
+#pragma unroll
+                        for (int b2 = a + 1; b2 < B; b2++) red[b2] = fmaf(dl, red[q++], red[b2]);
+                        const float *srow = Ss + (f0 + a) * D + j;
+#pragma unroll
+                        for (int i = 0; i < KPL; i++) g[i] = fmaf(dl, srow[i * G], g[i]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < E; e++)
+#pragma unroll
+                    for (int a = 0; a < B; a++) pred[e] = fmaf(dls[a], ye[e][a], pred[e]);
             }
         }
         if (act) {
@@ -543,8 +580,8 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     return GORSE_B200_OK;
 }
 
-template <int G, int E, int KPL>
-static int32_t launch_group(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
+template <int G, int E, int KPL, int B>
+static int32_t launch_group_b(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
                             const int32_t *rows, int32_t n_rows)
 {
     gorse_b200_ctx *c = cf->ctx;
@@ -555,10 +592,25 @@ static int32_t launch_group(gorse_b200_cf *cf, float *X, const float *Y, const i
     const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (32 * warps), (227 * 1024) / (sm + 1024)));
     const int groups_per_cta = warps * (32 / G);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_rows + groups_per_cta - 1) / groups_per_cta, (int64_t)c->sm_count * ctas_per_sm));
-    GB_CUDA(cudaFuncSetAttribute(als_rows_group_kernel<G, E, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    als_rows_group_kernel<G, E, KPL><<<grid, 32 * warps, sm, c->stream>>>(X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows);
+    GB_CUDA(cudaFuncSetAttribute(als_rows_group_kernel<G, E, KPL, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    als_rows_group_kernel<G, E, KPL, B><<<grid, 32 * warps, sm, c->stream>>>(X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows);
     GB_LAUNCHED(c);
     return GORSE_B200_OK;
+}
+
+// coordinates resolved per butterfly: 4 by default; GORSE_B200_ALS_BLOCK=1 is the plain one-at-a-time sweep (A/B runs)
+static int als_block()
+{
+    static int b = [] { const char *e = getenv("GORSE_B200_ALS_BLOCK"); return e && atoi(e) == 1 ? 1 : 4; }();
+    return b;
+}
+
+template <int G, int E, int KPL>
+static int32_t launch_group(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
+                            const int32_t *rows, int32_t n_rows)
+{
+    if (als_block() == 1) return launch_group_b<G, E, KPL, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+    return launch_group_b<G, E, KPL, 4>(cf, X, Y, off, idx, reg, w, rows, n_rows);
 }
 
 template <int G, int E>

@@ -227,6 +227,30 @@ int32_t gorse_b200_index_search_indices(gorse_b200_index *ix, const int64_t *q_i
 int32_t gorse_b200_index_search_range(gorse_b200_index *ix, int64_t q0, int64_t q1, int32_t k, int32_t prune0,
                                       int32_t *idx_out, float *dist_out, int32_t *count_out);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Similarity vectors and scores: the host logic of logics.item_to_item / logics.user_to_user
+ * around the neighbour search.  Pure host functions except _index_query_similar.
+ * ---------------------------------------------------------------------------------------- */
+/* dense embedding as the reference stores it: bfloats.FromFloat32 + ToFloat32
+ * (common/bfloats/bfloats.go:23-37; logics/item_to_item.go:151-164).  in == out is allowed. */
+int32_t gorse_b200_bf16_truncate(const float *in, int64_t n, float *out);
+/* appendSparseVector (logics/vector_writer.go:200-209): ids outside [0, n_idf) or with idf <= 0 are
+ * skipped; value = (float)sqrt((double)idf[id]); index = offset + id ("auto" appends users after tags
+ * with offset = len(tagsIDF), logics/item_to_item.go:238-239).  Outputs hold up to n_ids entries. */
+int32_t gorse_b200_sparse_vector(const int32_t *ids, int32_t n_ids, const float *idf, int32_t n_idf, uint32_t offset,
+                                 uint32_t *indices_out, float *values_out, int32_t *count_out);
+/* QueryItemToItem / QueryUserToUser score post-processing (logics/item_to_item.go:63-85,
+ * logics/user_to_user.go:63-85) applied to one result row of this library (ascending distance,
+ * id -1 padding): drop self_id; NEG_DOT: drop dot <= 0, score = dot * scale; EUCLIDEAN:
+ * score = 1 / (1 + dist * scale); stop at n.  score_scale is 0.5 for type "auto", else 1. */
+int32_t gorse_b200_similar_scores(int32_t metric, double score_scale, int32_t self_id, int32_t n, const int32_t *nbr_ids,
+                                  const float *nbr_dist, int32_t n_nbr, int32_t *ids_out, double *scores_out, int32_t *count_out);
+/* QueryItemToItem for the stored vectors [q0, q1): ids_out / scores_out are (q1-q0) x n (id -1 padding),
+ * count_out[q1-q0] */
+int32_t gorse_b200_index_query_similar(gorse_b200_index *ix, int64_t q0, int64_t q1, int32_t n, double score_scale,
+                                       int32_t *ids_out, double *scores_out, int32_t *count_out);
+
 #ifdef __cplusplus
 }
 #endif

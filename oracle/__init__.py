@@ -90,6 +90,11 @@ def _sig(L):
     L.gbo_evaluate.argtypes = [F32, F32, C.c_int32, C.c_int32, I64, I32, I64, I32, C.c_int32, F32]
     L.gbo_ref_bind.restype = C.c_int32
     L.gbo_ref_bind.argtypes = [C.c_char_p]
+    L.gbo_bf16_truncate.argtypes = [F32, C.c_int64, F32]
+    L.gbo_sparse_vector.restype = C.c_int32
+    L.gbo_sparse_vector.argtypes = [I32, C.c_int32, F32, C.c_int32, C.c_uint32, _p(np.uint32), F32]
+    L.gbo_similar_scores.restype = C.c_int32
+    L.gbo_similar_scores.argtypes = [C.c_int32, C.c_double, C.c_int32, C.c_int32, I32, F32, C.c_int32, I32, _p(np.float64)]
 
 
 def f32(a):
@@ -182,6 +187,28 @@ def bruteforce_all(X, q0, q1, k, prune0=False, metric=METRIC_NEG_DOT, n_threads=
     oc = np.zeros(nq, np.int32)
     sec = lib().gbo_bruteforce_all(X, X.shape[0], X.shape[1], q0, q1, k, int(prune0), metric, n_threads, oi, os_, oc)
     return oi, os_, oc, sec
+
+
+def bf16_truncate(a):
+    a = f32(a)
+    out = np.empty_like(a)
+    lib().gbo_bf16_truncate(a.reshape(-1), a.size, out.reshape(-1))
+    return out
+
+
+def sparse_vector(ids, idf, offset=0):
+    ids, idf = i32(ids), f32(idf)
+    ind, val = np.zeros(len(ids), np.uint32), np.zeros(len(ids), np.float32)
+    m = lib().gbo_sparse_vector(ids, len(ids), idf, len(idf), offset, ind, val)
+    return ind[:m], val[:m]
+
+
+def similar_scores(euclidean, score_scale, self_id, n, nbr_ids, nbr_score):
+    """logics.QueryItemToItem post-processing; nbr_score is the vector store's "higher is closer" score."""
+    nbr_ids, nbr_score = i32(nbr_ids), f32(nbr_score)
+    ids, sc = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.float64)
+    m = lib().gbo_similar_scores(int(euclidean), float(score_scale), int(self_id), int(n), nbr_ids, nbr_score, len(nbr_ids), ids, sc)
+    return ids[:m], sc[:m]
 
 
 def evaluate(P, Q, test_off, test_items, neg_off, neg_items, topk):

@@ -766,6 +766,58 @@ double gbo_bruteforce_all(const float *X, int64_t N, int32_t d, int64_t q0, int6
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Similarity vectors and scores: logics/item_to_item.go, logics/user_to_user.go, logics/vector_writer.go
+ * ---------------------------------------------------------------------------------------- */
+/* dense embedding as stored: bfloats.FromFloat32 keeps the high 16 bits (common/bfloats/bfloats.go:23-29),
+ * bfloats.ToFloat32 widens them again (:31-37); logics/item_to_item.go:151-164 ExtractItemEmbedding */
+void gbo_bf16_truncate(const float *in, int64_t n, float *out)
+{
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t u;
+        memcpy(&u, &in[i], 4);
+        u = (uint32_t)((uint16_t)(u >> 16)) << 16;
+        memcpy(&out[i], &u, 4);
+    }
+}
+
+/* appendSparseVector (logics/vector_writer.go:200-209): ids outside [0, len(idf)) or with idf <= 0 are skipped;
+ * value = float32(math.Sqrt(float64(idf[id]))); "auto" calls it twice, the second time with offset = len(tagsIDF)
+ * (logics/item_to_item.go:238-239).  Returns the number of entries appended. */
+int32_t gbo_sparse_vector(const int32_t *ids, int32_t n_ids, const float *idf, int32_t n_idf, uint32_t offset,
+                          uint32_t *indices_out, float *values_out)
+{
+    int32_t m = 0;
+    for (int32_t t = 0; t < n_ids; t++) {
+        int32_t id = ids[t];
+        if (id < 0 || id >= n_idf || idf[id] <= 0) continue;
+        indices_out[m] = offset + (uint32_t)id;
+        values_out[m] = (float)sqrt((double)idf[id]);
+        m++;
+    }
+    return m;
+}
+
+/* QueryItemToItem / QueryUserToUser post-processing (logics/item_to_item.go:63-85, user_to_user.go:63-85).
+ * Input: the neighbours as the vector store returned them for a query of n+1, score = "higher is closer"
+ * (Dot: the dot product; Euclidean: the NEGATED distance, storage/vectors/database.go:101).  Drops the query's own
+ * id, drops score <= 0 for Dot, scales, maps Euclidean to 1/(1 - score) = 1/(1 + dist), stops at n. */
+int32_t gbo_similar_scores(int32_t euclidean, double score_scale, int32_t self_id, int32_t n,
+                           const int32_t *nbr_ids, const float *nbr_score, int32_t n_nbr,
+                           int32_t *ids_out, double *scores_out)
+{
+    int32_t m = 0;
+    for (int32_t t = 0; t < n_nbr && m < n; t++) {
+        if (nbr_ids[t] == self_id || (!euclidean && nbr_score[t] <= 0)) continue;
+        double score = (double)nbr_score[t] * score_scale;
+        if (euclidean) score = 1 / (1 - score);
+        ids_out[m] = nbr_ids[t];
+        scores_out[m] = score;
+        m++;
+    }
+    return m;
+}
+
+/* ------------------------------------------------------------------------------------------
  * Metrics + Evaluate: model/cf/evaluator.go
  * ---------------------------------------------------------------------------------------- */
 static inline int in_set(const int32_t *t, int32_t n, int32_t v)

@@ -91,6 +91,14 @@ double gbo_bruteforce_all(const float *X, int64_t N, int32_t d, int64_t q0, int6
                           int32_t *out_idx, float *out_score, int32_t *out_count);
 
 /* ---- model/cf/evaluator.go ---- */
+/* logics: similarity vectors and scores (item_to_item.go, user_to_user.go, vector_writer.go) */
+void gbo_bf16_truncate(const float *in, int64_t n, float *out);                                    /* bfloats.go:23-37 */
+int32_t gbo_sparse_vector(const int32_t *ids, int32_t n_ids, const float *idf, int32_t n_idf, uint32_t offset,
+                          uint32_t *indices_out, float *values_out);                               /* vector_writer.go:200-209 */
+int32_t gbo_similar_scores(int32_t euclidean, double score_scale, int32_t self_id, int32_t n,
+                           const int32_t *nbr_ids, const float *nbr_score, int32_t n_nbr,
+                           int32_t *ids_out, double *scores_out);                                  /* item_to_item.go:63-85 */
+
 float gbo_ndcg(const int32_t *target, int32_t n_target, const int32_t *rank, int32_t n_rank);      /* :75-89 */
 float gbo_precision(const int32_t *target, int32_t n_target, const int32_t *rank, int32_t n_rank); /* :94-102 */
 float gbo_recall(const int32_t *target, int32_t n_target, const int32_t *rank, int32_t n_rank);    /* :108-116 */

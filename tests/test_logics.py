@@ -1,0 +1,53 @@
+"""Host logic around the neighbour search: dense bf16 embeddings, sqrt(idf) sparse vectors and
+the QueryItemToItem / QueryUserToUser score post-processing.  CPU only: the oracle's restatement against values
+lifted from the reference, and the library's host functions against the oracle (bit-exact)."""
+import numpy as np
+
+
+def test_oracle_bf16_matches_the_reference_definition(orc):
+    # bfloats.FromFloat32 keeps bits 31..16 (common/bfloats/bfloats.go:23-29); ToFloat32 shifts them back (:31-37)
+    a = np.array([0.1, 0.2, 0.3, 1.0, -2.7, 3.0e38, 1e-40, 0.0, -0.0], np.float32)
+    want = (a.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+    got = orc.bf16_truncate(a)
+    assert got.tobytes() == want.tobytes()
+    assert got[:3].tolist() == [0.099609375, 0.19921875, 0.298828125]
+
+
+def test_oracle_sparse_vector(orc):
+    # logics/vector_writer.go:200-209: skip id < 0, id >= len(idf), idf <= 0; value = float32(sqrt(float64(idf)))
+    idf = np.array([4.0, 0.0, 2.0, 9.0, -1.0], np.float32)
+    ind, val = orc.sparse_vector([0, 3, -1, 9, 2, 1, 4], idf)
+    assert ind.tolist() == [0, 3, 2] and val.tolist() == [2.0, 3.0, np.float32(np.sqrt(2.0))]
+    # "auto": users appended after tags with offset = len(tagsIDF) (logics/item_to_item.go:238-239)
+    ind2, _ = orc.sparse_vector([2, 0], idf, offset=7)
+    assert ind2.tolist() == [9, 7]
+
+
+def test_oracle_similar_scores(orc):
+    # logics/item_to_item.go:63-85.  Euclidean: store score = -distance -> 1/(1+dist); own id dropped; stops at n
+    ids, sc = orc.similar_scores(True, 1.0, 0, 3, [0, 5, 6, 7, 8], np.float32([0, -1, -2, -3, -4]))
+    assert ids.tolist() == [5, 6, 7] and sc.tolist() == [0.5, 1 / 3, 0.25]
+    # Dot, type "auto" (x0.5): score <= 0 dropped
+    ids, sc = orc.similar_scores(False, 0.5, 0, 3, [5, 0, 6, 7, 8], np.float32([9, 8, 0, -3, 4]))
+    assert ids.tolist() == [5, 8] and sc.tolist() == [4.5, 2.0]
+
+
+def test_library_host_functions_match_the_oracle(gb, orc):
+    rng = np.random.default_rng(0)
+    a = (rng.standard_normal(5000) * 10.0 ** rng.integers(-20, 20, 5000)).astype(np.float32)
+    assert gb.bf16_truncate(a).tobytes() == orc.bf16_truncate(a).tobytes()
+    idf = rng.random(300).astype(np.float32) * (rng.random(300) > 0.2)
+    ids = rng.integers(-5, 320, 500).astype(np.int32)
+    gi, gv = gb.sparse_vector(ids, idf, offset=123)
+    oi, ov = orc.sparse_vector(ids, idf, offset=123)
+    assert gi.tobytes() == oi.tobytes() and gv.tobytes() == ov.tobytes()
+    for metric, euclid in ((gb.METRIC_EUCLIDEAN, True), (gb.METRIC_NEG_DOT, False)):
+        for scale in (1.0, 0.5):
+            nbr = rng.permutation(50).astype(np.int32)[:21]
+            dist = np.sort(rng.standard_normal(21).astype(np.float32) + (1.5 if euclid else 0.0))
+            if euclid:
+                dist = np.abs(dist)
+                dist.sort()
+            g_ids, g_sc = gb.similar_scores(metric, scale, int(nbr[3]), 10, nbr, dist)
+            o_ids, o_sc = orc.similar_scores(euclid, scale, int(nbr[3]), 10, nbr, -dist)
+            assert g_ids.tolist() == o_ids.tolist() and g_sc.tobytes() == o_sc.tobytes()
