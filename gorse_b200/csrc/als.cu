@@ -217,6 +217,12 @@ als_rows_kernel(float *X, const float *Y, int d, int32_t x_lo, int32_t y_lo, con
 // shared memory as [t][d+1] (conflict-free both along a row and down a column) next to one copy of S per CTA.
 // Differences from the reference are reassociation (lane-parallel sums, incremental g) and one reciprocal-multiply
 // instead of a divide: observed ~1e-6 relative, budget 1e-4.
+// floats of shared memory per lane group; padded so that the groups of one warp start G banks apart
+__host__ __device__ constexpr int group_stage_floats(int G, int E, int DP)
+{
+    return G * E * DP + ((G < 32 && (G * E * DP) % 32 == 0) ? G : 0);
+}
+
 template <int G>
 __device__ __forceinline__ float group_sum(float v)
 {
@@ -235,7 +241,7 @@ als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_
     float *Ss = smem;                                   // [D][D]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int grp = lane / G, j = lane % G;
-    float *ys = smem + D * D + (size_t)(wid * NG + grp) * (G * E * DP);
+    float *ys = smem + D * D + (size_t)(wid * NG + grp) * group_stage_floats(G, E, DP);
     for (int e = threadIdx.x; e < D * D; e += blockDim.x) Ss[e] = S[e];
     __syncthreads();
     const float omw = 1.0f - w;
@@ -506,11 +512,21 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
 
 // rows bucketed by length, one launch per class:
 //   lane-group form (d % 32 == 0, d <= 128; als_rows_group_kernel):  n <= 8 | n <= 32 | n <= 96 | longer -> Gram form
+//                                                   (GORSE_B200_ALS_G16=1:  n <= 8 | n <= 16 | n <= 32 | n <= 96)
 //   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp) | - |
 //   longer -> Gram form when d <= 128, else gathered from L2 without staging
 static const int kStageFloats[2] = {3072, 12288};
-static const int kGroupRows[3] = {8, 32, 96};
-#define GB_ALS_LONG 3   // index of the long-row class
+#define GB_ALS_LONG 4   // index of the long-row class
+// lane-group classes: rows up to max_n entries run with G lanes per row and E entries per lane
+struct GroupClass { int max_n, G, E; };
+static const GroupClass kGroupWide[4] = {{8, 8, 1}, {32, 32, 1}, {96, 32, 3}, {0, 0, 0}};
+static const GroupClass kGroupFine[4] = {{8, 8, 1}, {16, 16, 1}, {32, 16, 2}, {96, 32, 3}};
+// GORSE_B200_ALS_G16=1: 9..32-entry rows share a warp two by two (16 lanes each) instead of taking a whole warp
+static const GroupClass *group_classes()
+{
+    static const GroupClass *t = [] { const char *e = getenv("GORSE_B200_ALS_G16"); return e && atoi(e) == 1 ? kGroupFine : kGroupWide; }();
+    return t;
+}
 
 static bool als_grouped(const gorse_b200_cf *cf) { return cf->d % 32 == 0 && cf->d <= 128; }
 
@@ -522,15 +538,18 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     for (int side = 0; side < 2; side++) {
         const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
         int32_t rows = side == 0 ? cf->n_users : cf->n_items;
-        std::vector<int32_t> cls[4];
+        std::vector<int32_t> cls[5];
         for (int32_t r = 0; r < rows; r++) {
             int64_t n = off[(size_t)r + 1] - off[r];
             int k;
-            if (grouped) k = n <= kGroupRows[0] ? 0 : n <= kGroupRows[1] ? 1 : n <= kGroupRows[2] ? 2 : GB_ALS_LONG;
-            else k = n * dp <= kStageFloats[0] ? 0 : n * dp <= kStageFloats[1] ? 1 : GB_ALS_LONG;
+            if (grouped) {
+                const GroupClass *gc = group_classes();
+                k = GB_ALS_LONG;
+                for (int q = 0; q < 4; q++) if (gc[q].G && n <= gc[q].max_n) { k = q; break; }
+            } else k = n * dp <= kStageFloats[0] ? 0 : n * dp <= kStageFloats[1] ? 1 : GB_ALS_LONG;
             cls[k].push_back(r);
         }
-        for (int k = 0; k < 4; k++) {
+        for (int k = 0; k < 5; k++) {
             // longest rows first inside a class: better tail behaviour
             std::stable_sort(cls[k].begin(), cls[k].end(), [&](int32_t a, int32_t b) {
                 return off[(size_t)a + 1] - off[a] > off[(size_t)b + 1] - off[b];
@@ -586,7 +605,7 @@ static int32_t launch_group_b(gorse_b200_cf *cf, float *X, const float *Y, const
 {
     gorse_b200_ctx *c = cf->ctx;
     constexpr int D = G * KPL, DP = D + 1;
-    const size_t s_bytes = sizeof(float) * D * D, per_warp = sizeof(float) * 32 * E * DP;
+    const size_t s_bytes = sizeof(float) * D * D, per_warp = sizeof(float) * (32 / G) * group_stage_floats(G, E, DP);
     const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024 - s_bytes) / per_warp));
     const size_t sm = s_bytes + warps * per_warp;
     const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (32 * warps), (227 * 1024) / (sm + 1024)));
@@ -630,7 +649,7 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
 {
     gorse_b200_ctx *c = cf->ctx;
     const bool grouped = als_grouped(cf);
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 5; k++) {
         int32_t n_rows = cf->als_rows_n[side][k];
         if (n_rows == 0) continue;
         const int32_t *rows = cf->als_rows[side][k].p;
@@ -651,8 +670,11 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             continue;
         }
         if (grouped && k != GB_ALS_LONG) {
-            if (k == 0) GB_TRY((launch_group_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-            else if (k == 1) GB_TRY((launch_group_d<32, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            const GroupClass gc = group_classes()[k];
+            if (gc.G == 8) GB_TRY((launch_group_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else if (gc.G == 16 && gc.E == 1) GB_TRY((launch_group_d<16, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else if (gc.G == 16) GB_TRY((launch_group_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else if (gc.E == 1) GB_TRY((launch_group_d<32, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else GB_TRY((launch_group_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             continue;
         }
