@@ -120,3 +120,38 @@ func (b *B200Bruteforce) AllNeighbors(q0, q1, k int, prune0 bool) ([][]lo.Tuple2
 	}
 	return out, nil
 }
+
+// SimilarScore is one (row, score) of QuerySimilar; the caller maps rows back to item / user ids.
+type SimilarScore struct {
+	Row   int
+	Score float64
+}
+
+// QuerySimilar is logics.QueryItemToItem / logics.QueryUserToUser (logics/item_to_item.go:50-86,
+// logics/user_to_user.go:50-86) for every stored vector in [q0, q1) in one call: the n nearest neighbours without the
+// vector itself, Dot scores <= 0 dropped, Euclidean mapped to 1/(1+dist); scoreScale is .5 for type "auto".
+func (b *B200Bruteforce) QuerySimilar(q0, q1, n int, scoreScale float64) ([][]SimilarScore, error) {
+	nq := q1 - q0
+	ids, scores, cnt := make([]int32, max(nq*n, 1)), make([]float64, max(nq*n, 1)), make([]int32, max(nq, 1))
+	st := C.gorse_b200_index_query_similar(b.ix, C.int64_t(q0), C.int64_t(q1), C.int32_t(n), C.double(scoreScale),
+		(*C.int32_t)(unsafe.Pointer(&ids[0])), (*C.double)(unsafe.Pointer(&scores[0])), (*C.int32_t)(unsafe.Pointer(&cnt[0])))
+	if st != 0 {
+		return nil, errors.New(C.GoString(C.gorse_b200_last_error()))
+	}
+	out := make([][]SimilarScore, nq)
+	for r := range out {
+		out[r] = make([]SimilarScore, cnt[r])
+		for t := range out[r] {
+			out[r][t] = SimilarScore{Row: int(ids[r*n+t]), Score: scores[r*n+t]}
+		}
+	}
+	return out, nil
+}
+
+// TruncateBF16 stores a dense embedding the way the reference does (bfloats.FromFloat32 + ToFloat32,
+// logics/item_to_item.go:151-164); vectors added this way are represented exactly by the index's bf16 tensor-core mirror.
+func TruncateBF16(v []float32) {
+	if len(v) > 0 {
+		C.gorse_b200_bf16_truncate((*C.float)(unsafe.Pointer(&v[0])), C.int64_t(len(v)), (*C.float)(unsafe.Pointer(&v[0])))
+	}
+}
