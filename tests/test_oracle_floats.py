@@ -126,3 +126,28 @@ def test_exp_accuracy(orc):
     assert orc.exp(np.float32(0)) == np.float32(1)
     assert np.isinf(orc.exp(np.float32(89.0)))       # overflow -> +Inf -> NaN gradient
     assert orc.exp(np.float32(-200.0)) == np.float32(0)
+
+
+@pytest.mark.parametrize("d", [16, 32, 64, 128])
+def test_bpr_step_through_the_reference_kernels(orc, d):
+    """BPR.Fit's per-triple call sequence (model/cf/model.go:469-488) executed with the REFERENCE'S OWN compiled
+    kernels (oracle/_ref: _mm512_dot, _mm512_mul_const_to, _mm512_mul_const_add, _mm512_sub_to, _mm512_mul_const) against
+    the oracle's restatement of the same step, one thread, same triple stream: factors must agree bit for bit."""
+    if not orc.ref_available():
+        pytest.skip("oracle/_ref not built (reference not mounted)")
+    if "avx512f" not in open("/proc/cpuinfo").read():
+        pytest.skip("host has no AVX-512")
+    from gorse_b200 import synth
+
+    assert orc.ref_bind()
+    U, I = 300, 120
+    off, items = synth.make_feedback(U, I, 4000, seed=d)
+    act = np.nonzero(np.diff(off) > 0)[0].astype(np.int32)
+    rng = np.random.default_rng(d)
+    P0 = (rng.standard_normal((U, d)) * 0.3).astype(np.float32)   # large enough that the sigmoid gradient is not ~0.5
+    Q0 = (rng.standard_normal((I, d)) * 0.3).astype(np.float32)
+    Pa, Qa, Pb, Qb = P0.copy(), Q0.copy(), P0.copy(), Q0.copy()
+    orc.bpr_epoch_threads(Pa, Qa, off, items, act, 42, 20000, 0.05, 0.01, 1, use_ref=False)
+    orc.bpr_epoch_threads(Pb, Qb, off, items, act, 42, 20000, 0.05, 0.01, 1, use_ref=True)
+    assert not np.array_equal(Pa, P0)
+    assert Pa.tobytes() == Pb.tobytes() and Qa.tobytes() == Qb.tobytes()
