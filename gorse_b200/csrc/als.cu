@@ -6,11 +6,15 @@
 // Roofline class: HBM bandwidth (one gather of the opposite table's rows per feedback + own row + one
 // Gram pass): B_epoch = 2|R|(4d+4) + 3(U+I)4d bytes.
 //
-// Row kernel: one warp per row.  The gathered rows Y[R_x] are staged once in shared memory
-// ([n][d+1], the +1 makes the per-f column walk conflict-free), the running predictions live in
-// registers, and the strictly sequential f loop costs two warp reductions per factor.  Sums over the
-// row's feedback are taken lane-parallel, so a/c/b differ from the reference's serial order by
-// reassociation only (parity budget 1e-4 relative, observed ~1e-6).
+// Row updates come in three forms, chosen per row by its length (prepare_als):
+//   * als_rows_group_kernel (d % 32 == 0, d <= 128, rows up to 96 entries): a group of 8/16/32 lanes per row, g = S x
+//     kept current in registers, B coordinates resolved per shuffle butterfly (see the comment at the kernel);
+//   * Gram form for longer rows (als_chunk_gram_kernel + als_solve_kernel): one Gauss-Seidel sweep on A x = h;
+//   * als_rows_kernel, one warp per row with the reference's loop structure, for the remaining shapes (d not a
+//     multiple of 32 or > 128).  The gathered rows Y[R_x] are staged once in shared memory ([n][d+1], the +1 makes the
+//     per-f column walk conflict-free), the running predictions live in registers.
+// In all forms sums over the row's feedback are taken lane-parallel, so results differ from the reference's serial
+// order by reassociation only (parity budget 1e-4 relative, observed ~1e-6).
 #include <algorithm>
 
 #include "cf.cuh"
@@ -511,8 +515,8 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
 }
 
 // rows bucketed by length, one launch per class:
-//   lane-group form (d % 32 == 0, d <= 128; als_rows_group_kernel):  n <= 8 | n <= 32 | n <= 96 | longer -> Gram form
-//                                                   (GORSE_B200_ALS_G16=1:  n <= 8 | n <= 16 | n <= 32 | n <= 96)
+//   lane-group form (d % 32 == 0, d <= 128; als_rows_group_kernel):  n <= 8 | n <= 16 | n <= 32 | n <= 96 | longer -> Gram form
+//                                                   (GORSE_B200_ALS_G16=0:  n <= 8 | n <= 32 | n <= 96)
 //   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp) | - |
 //   longer -> Gram form when d <= 128, else gathered from L2 without staging
 static const int kStageFloats[2] = {3072, 12288};
@@ -521,10 +525,11 @@ static const int kStageFloats[2] = {3072, 12288};
 struct GroupClass { int max_n, G, E; };
 static const GroupClass kGroupWide[4] = {{8, 8, 1}, {32, 32, 1}, {96, 32, 3}, {0, 0, 0}};
 static const GroupClass kGroupFine[4] = {{8, 8, 1}, {16, 16, 1}, {32, 16, 2}, {96, 32, 3}};
-// GORSE_B200_ALS_G16=1: 9..32-entry rows share a warp two by two (16 lanes each) instead of taking a whole warp
+// default: 9..32-entry rows share a warp two by two (16 lanes each): 2.5 instead of 6 shuffles per row and coordinate,
+// 33.7 vs 43-47 ms/epoch at C3.  GORSE_B200_ALS_G16=0 gives such rows a whole warp each (A/B runs).
 static const GroupClass *group_classes()
 {
-    static const GroupClass *t = [] { const char *e = getenv("GORSE_B200_ALS_G16"); return e && atoi(e) == 1 ? kGroupFine : kGroupWide; }();
+    static const GroupClass *t = [] { const char *e = getenv("GORSE_B200_ALS_G16"); return e && atoi(e) == 0 && *e == '0' ? kGroupWide : kGroupFine; }();
     return t;
 }
 
@@ -617,10 +622,13 @@ static int32_t launch_group_b(gorse_b200_cf *cf, float *X, const float *Y, const
     return GORSE_B200_OK;
 }
 
-// coordinates resolved per butterfly: 4 by default; GORSE_B200_ALS_BLOCK=1 is the plain one-at-a-time sweep (A/B runs)
+// coordinates resolved per butterfly: 1 by default.  GORSE_B200_ALS_BLOCK=4 resolves four per butterfly (10 interleaved
+// reductions, a 4x shorter dependent chain) -- measured SLOWER at C3 (72 vs 43 ms/epoch): the row kernels are bound by
+// shuffle/shared-memory issue (the LSU pipe), not by the chain's latency, and the blocked form executes 13.5 instead of 6
+// shuffles per coordinate.  Kept for A/B runs.
 static int als_block()
 {
-    static int b = [] { const char *e = getenv("GORSE_B200_ALS_BLOCK"); return e && atoi(e) == 1 ? 1 : 4; }();
+    static int b = [] { const char *e = getenv("GORSE_B200_ALS_BLOCK"); return e && atoi(e) == 4 ? 4 : 1; }();
     return b;
 }
 
