@@ -5,15 +5,15 @@
 O=gpurun_out/round_check
 mkdir -p $O
 step() { echo "== $1"; }
-step "ALS parity, one coordinate per butterfly"
-GORSE_B200_ALS_BLOCK=1 timeout 60 python -m pytest tests/test_als_gpu.py -x -q 2>&1 | tail -2
-step "ALS parity, 16-lane classes"
-GORSE_B200_ALS_G16=1 timeout 60 python -m pytest tests/test_als_gpu.py -x -q 2>&1 | tail -2
-step "ALS C3 bench: default / block=1 / g16"
+step "ALS parity, four coordinates per butterfly"
+GORSE_B200_ALS_BLOCK=4 timeout 60 python -m pytest tests/test_als_gpu.py -x -q 2>&1 | tail -2
+step "ALS parity, whole-warp classes"
+GORSE_B200_ALS_G16=0 timeout 60 python -m pytest tests/test_als_gpu.py -x -q 2>&1 | tail -2
+step "ALS C3 bench: default / block=4 / whole-warp classes"
 timeout 60 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/bench_c3.json 2> $O/bench_c3.err
-GORSE_B200_ALS_BLOCK=1 timeout 60 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/bench_c3_block1.json 2>> $O/bench_c3.err
-GORSE_B200_ALS_G16=1 timeout 60 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/bench_c3_g16.json 2>> $O/bench_c3.err
-for f in $O/bench_c3.json $O/bench_c3_block1.json $O/bench_c3_g16.json; do python - "$f" <<'PY'
+GORSE_B200_ALS_BLOCK=4 timeout 60 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/bench_c3_block4.json 2>> $O/bench_c3.err
+GORSE_B200_ALS_G16=0 timeout 60 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/bench_c3_wide.json 2>> $O/bench_c3.err
+for f in $O/bench_c3.json $O/bench_c3_block4.json $O/bench_c3_wide.json; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
