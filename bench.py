@@ -399,51 +399,75 @@ def run_topk(args):
 
     N, d, k = (1_000_000, 128, 100) if not args.small else (100_000, 128, 100)
     nq = min(N, args.queries)
+    # N > 1: the vectors are replicated, rank r answers its own nq query rows, no collective (weak scaling)
+    rank, world, local = dist_env()
+    assert world == args.gpus or world == 1, f"WORLD_SIZE {world} != --gpus {args.gpus}"
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    q_lo = (rank * nq) % max(1, N - nq + 1)
     rng = np.random.default_rng(0)
     X = rng.standard_normal((N, d), dtype=np.float32)
     X /= np.linalg.norm(X, axis=1, keepdims=True)
-    with gb.Context(0) as ctx, gb.BruteforceIndex(ctx, d, gb.METRIC_NEG_DOT) as ix:
+    with gb.Context(local) as ctx, gb.BruteforceIndex(ctx, d, gb.METRIC_NEG_DOT) as ix:
         ix.add(X)
         ix.search_range(0, 512, k)  # builds the bf16 mirror
         # results land in page-locked host buffers, like the shim's pinned mirror (gorse_b200_host_alloc)
         pin = (gb.PinnedArray((nq, k), np.int32), gb.PinnedArray((nq, k), np.float32), gb.PinnedArray((nq,), np.int32))
         out = (pin[0].array, pin[1].array, pin[2].array)
         for _ in range(max(0, args.warmup - 1)):
-            ix.search_range(0, nq, k, out=out)
-        sampler = ClockSampler(0)
+            ix.search_range(q_lo, q_lo + nq, k, out=out)
+        if dist:
+            dist.barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
         ix.debug_stage1()
         l0, t0 = ctx.launch_count(), time.time()
         ms_list = []
         for s in range(args.steps):
             ctx.timer_begin()
-            idx, dist, cnt = ix.search_range(0, nq, k, out=out)   # host buffers out: this IS the end-to-end call
+            idx, dist_, cnt = ix.search_range(q_lo, q_lo + nq, k, out=out)   # host buffers out: this IS the end-to-end call
             ms_list.append(ctx.timer_end())
         t1 = time.time()
         launches = ctx.launch_count() - l0
         fb = ix.debug_fallback_rows()
         s1_ms, s1_flop = ix.debug_stage1()
-        clocks = sampler.stop(t0, t1)
+        clocks = sampler.stop(t0, t1) if sampler else None
     ms = float(np.mean(ms_list))
     assert cnt.min() == k
     cnt = None
     for p_ in pin:
         p_.free()
-    flop = 2.0 * nq * N * d
+    if dist:
+        import torch
+
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)   # device-timed, max over ranks
+        ms = float(t.item())
+        dist.barrier()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+    nq_all = nq * world
+    flop = 2.0 * nq_all * N * d
     peak = 1427.2
     pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
         peak = float(json.load(open(pp)).get("bf16_tflops_sustained", peak))
     cb = None
-    if not args.no_cpu:
+    if not args.no_cpu and world == 1:
         cores = len(os.sched_getaffinity(0))
         sample = 4 * cores
         _, _, _, sec = oracle.bruteforce_all(X, 0, sample, k, metric=oracle.METRIC_NEG_DOT, n_threads=cores)
         cb = {"value": sample / sec, "unit": "vectors/s", "cores": cores, "kind": "port",
               "sample": f"{sample} queries of the same 1M set: reference-order dot + Go heap per query, {cores} threads, {sec:.2f} s"}
-    print(json.dumps({"metric": "item-to-item top-k vectors/sec", "value": nq / (ms * 1e-3), "unit": "vectors/s", "n_gpus": 1, "steps": args.steps,
+    print(json.dumps({"metric": "item-to-item top-k vectors/sec", "value": nq_all / (ms * 1e-3), "unit": "vectors/s", "n_gpus": world, "steps": args.steps,
                       "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                       "dtype": "bf16 tensor-core candidate generation + f32 exact re-rank", "data": "synthetic",
-                      "config": {"workload": f"all-pairs top-{k} over {N} x {d} unit vectors, {nq} query rows per step (BASELINE configs[3])",
+                      "config": {"workload": f"all-pairs top-{k} over {N} x {d} unit vectors, {nq} query rows per step and rank (BASELINE configs[3])"
+                                             + (f" x {world} ranks, vectors replicated, queries sharded, no collective" if world > 1 else ""),
                                  "metric": "-dot (cosine on unit vectors)", "fallback_rows": int(fb)},
                       "roofline": {"bound": "tensor", "achieved": s1_flop / (s1_ms * 1e-3) / 1e12, "peak": peak, "unit": "TFLOP/s",
                                    "frac": s1_flop / (s1_ms * 1e-3) / 1e12 / peak, "traffic": None, "kernel": "mma::topk_mma_kernel<4>",
@@ -451,7 +475,7 @@ def run_topk(args):
                                    "whole_call_tflops": flop / (ms * 1e-3) / 1e12,
                                    "note": "dominant kernel = the tcgen05 sweep (CUDA events on the library's stream); algorithmic flop 2*nq*N*d; "
                                            "peak = measured sustained bf16 (MEASURED_PEAKS.json). whole_call adds query mirror, prune, exact re-rank, fallback and result D2H"},
-                      "cpu_baseline": cb, "e2e": {"value": nq / (ms * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": 0,
+                      "cpu_baseline": cb, "e2e": {"value": nq_all / (ms * 1e-3), "unit": "vectors/s", "h2d_bytes_per_step": 0,
                                                   "d2h_bytes_per_step": nq * k * 8 + nq * 4},
                       "gpu_launches": int(launches), "clocks": clocks}), flush=True)
 
