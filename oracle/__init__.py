@@ -93,6 +93,11 @@ def _sig(L):
     L.gbo_bf16_truncate.argtypes = [F32, C.c_int64, F32]
     L.gbo_sparse_vector.restype = C.c_int32
     L.gbo_sparse_vector.argtypes = [I32, C.c_int32, F32, C.c_int32, C.c_uint32, _p(np.uint32), F32]
+    U32 = _p(np.uint32)
+    L.gbo_sparse_dot.restype = C.c_float
+    L.gbo_sparse_dot.argtypes = [U32, F32, C.c_int32, U32, F32, C.c_int32]
+    L.gbo_sparse_bruteforce_search.restype = C.c_int32
+    L.gbo_sparse_bruteforce_search.argtypes = [I64, U32, F32, C.c_int64, U32, F32, C.c_int32, C.c_int64, C.c_int32, I32, F32]
     L.gbo_similar_scores.restype = C.c_int32
     L.gbo_similar_scores.argtypes = [C.c_int32, C.c_double, C.c_int32, C.c_int32, I32, F32, C.c_int32, I32, _p(np.float64)]
 
@@ -201,6 +206,18 @@ def sparse_vector(ids, idf, offset=0):
     ind, val = np.zeros(len(ids), np.uint32), np.zeros(len(ids), np.float32)
     m = lib().gbo_sparse_vector(ids, len(ids), idf, len(idf), offset, ind, val)
     return ind[:m], val[:m]
+
+
+def sparse_bruteforce_search(off, indices, values, self_index, k):
+    """k best neighbours (ids, dots) of stored sparse vector `self_index` among the CSR-packed vectors."""
+    off = i64(off)
+    indices = np.ascontiguousarray(indices, np.uint32)
+    values = f32(values)
+    a, b = int(off[self_index]), int(off[self_index + 1])
+    oi, od = np.zeros(max(k, 1), np.int32), np.zeros(max(k, 1), np.float32)
+    m = lib().gbo_sparse_bruteforce_search(off, indices, values, len(off) - 1, indices[a:b].copy(), values[a:b].copy(), b - a,
+                                           self_index, k, oi, od)
+    return oi[:m].copy(), od[:m].copy()
 
 
 def similar_scores(euclidean, score_scale, self_id, n, nbr_ids, nbr_score):

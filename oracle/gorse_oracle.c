@@ -817,6 +817,50 @@ int32_t gbo_similar_scores(int32_t euclidean, double score_scale, int32_t self_i
     return m;
 }
 
+/* Sparse similarity search (the "tags" / "users" / "auto" item-to-item and user-to-user types): what the reference
+ * asks its vector store for with sparse vectors and the Dot metric (storage/vectors/xvec.go:244-248 flat sparse index,
+ * :405 query).  The arithmetic lives in gorse-io/xvec v0.0.0-20260821023012-cf0c34c6025f (go.mod:31), which is NOT under
+ * /root/reference: PARITY UNPINNED except for the neighbour-id orders the reference's tests assert
+ * (logics/item_to_item_test.go:212-316).  Restated as: indices ascending in every vector (item_to_item.go:191,213,
+ * 236-237 sort the ids before appendSparseVector), dot = merge-join summed in index order in fp32, the k largest dots
+ * through the same bounded Go heap as Bruteforce (distance = -dot, ties as container/heap leaves them). */
+float gbo_sparse_dot(const uint32_t *ia, const float *va, int32_t na, const uint32_t *ib, const float *vb, int32_t nb)
+{
+    float s = 0.0f;
+    int32_t a = 0, b = 0;
+    while (a < na && b < nb) {
+        if (ia[a] == ib[b]) { s = s + va[a] * vb[b]; a++; b++; }
+        else if (ia[a] < ib[b]) a++;
+        else b++;
+    }
+    return s;
+}
+
+/* neighbours of stored vector `self` (or of nothing stored when self < 0 and q_* given): ids and dots, best first */
+int32_t gbo_sparse_bruteforce_search(const int64_t *off, const uint32_t *indices, const float *values, int64_t N,
+                                     const uint32_t *q_ind, const float *q_val, int32_t q_n, int64_t self, int32_t k,
+                                     int32_t *out_idx, float *out_dot)
+{
+    gopq pq;
+    pq_init(&pq, 1, (int64_t)k + 2);
+    for (int64_t i = 0; i < N; i++) {
+        if (i == self) continue;
+        float dotv = gbo_sparse_dot(q_ind, q_val, q_n, indices + off[i], values + off[i], (int32_t)(off[i + 1] - off[i]));
+        pq_push(&pq, (int32_t)i, -dotv);
+        if (pq.h.n > k) (void)gh_pop(&pq.h);
+    }
+    gopq r;
+    pq_reverse(&pq, &r);
+    int32_t m = 0;
+    while (r.h.n > 0) {
+        gbo_elem e = gh_pop(&r.h);
+        out_idx[m] = e.value; out_dot[m] = -e.weight; m++;
+    }
+    pq_free(&r);
+    pq_free(&pq);
+    return m;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Metrics + Evaluate: model/cf/evaluator.go
  * ---------------------------------------------------------------------------------------- */

@@ -99,6 +99,12 @@ int32_t gbo_similar_scores(int32_t euclidean, double score_scale, int32_t self_i
                            const int32_t *nbr_ids, const float *nbr_score, int32_t n_nbr,
                            int32_t *ids_out, double *scores_out);                                  /* item_to_item.go:63-85 */
 
+/* sparse Dot search (xvec flat sparse index, storage/vectors/xvec.go:244-248): parity unpinned beyond id orders */
+float gbo_sparse_dot(const uint32_t *ia, const float *va, int32_t na, const uint32_t *ib, const float *vb, int32_t nb);
+int32_t gbo_sparse_bruteforce_search(const int64_t *off, const uint32_t *indices, const float *values, int64_t N,
+                                     const uint32_t *q_ind, const float *q_val, int32_t q_n, int64_t self, int32_t k,
+                                     int32_t *out_idx, float *out_dot);
+
 float gbo_ndcg(const int32_t *target, int32_t n_target, const int32_t *rank, int32_t n_rank);      /* :75-89 */
 float gbo_precision(const int32_t *target, int32_t n_target, const int32_t *rank, int32_t n_rank); /* :94-102 */
 float gbo_recall(const int32_t *target, int32_t n_target, const int32_t *rank, int32_t n_rank);    /* :108-116 */

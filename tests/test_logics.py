@@ -51,3 +51,35 @@ def test_library_host_functions_match_the_oracle(gb, orc):
             g_ids, g_sc = gb.similar_scores(metric, scale, int(nbr[3]), 10, nbr, dist)
             o_ids, o_sc = orc.similar_scores(euclid, scale, int(nbr[3]), 10, nbr, -dist)
             assert g_ids.tolist() == o_ids.tolist() and g_sc.tobytes() == o_sc.tobytes()
+
+
+def _pack(vectors):
+    off = np.concatenate([[0], np.cumsum([len(v[0]) for v in vectors])]).astype(np.int64)
+    ind = np.concatenate([v[0] for v in vectors]).astype(np.uint32)
+    val = np.concatenate([v[1] for v in vectors]).astype(np.float32)
+    return off, ind, val
+
+
+def test_oracle_sparse_search_reference_known_answers(orc):
+    """logics/item_to_item_test.go:212-316 (TestTags, TestUsers, TestAuto): idf = 1, item i carries ids 1..100-i;
+    the 10 neighbours of item 0 are items 1..10; in "auto" even items carry tags and odd items users (offset
+    len(tagsIDF) = 101), so item 0 -> 2,4,..,20 and item 1 -> 3,5,..,21 (score x0.5, item_to_item.go:70-72)."""
+    idf = np.ones(101, np.float32)
+    vecs = [orc.sparse_vector(list(range(1, 101 - i)), idf) for i in range(100)]          # TestTags == TestUsers
+    off, ind, val = _pack(vecs)
+    ids, dots = orc.sparse_bruteforce_search(off, ind, val, 0, 11)
+    s_ids, s_sc = orc.similar_scores(False, 1.0, 0, 10, ids, dots)
+    assert s_ids.tolist() == list(range(1, 11)) and s_sc.tolist() == [float(100 - i) for i in range(1, 11)]
+    auto = []
+    for i in range(100):
+        tags = list(range(1, 101 - i)) if i % 2 == 0 else []
+        users = list(range(1, 101 - i)) if i % 2 == 1 else []
+        ti, tv = orc.sparse_vector(tags, idf)
+        ui, uv = orc.sparse_vector(users, idf, offset=len(idf))
+        auto.append((np.concatenate([ti, ui]), np.concatenate([tv, uv])))
+    off, ind, val = _pack(auto)
+    for q, want in ((0, [2 * i for i in range(1, 11)]), (1, [2 * i + 1 for i in range(1, 11)])):
+        ids, dots = orc.sparse_bruteforce_search(off, ind, val, q, 11)
+        s_ids, s_sc = orc.similar_scores(False, 0.5, q, 10, ids, dots)
+        assert s_ids.tolist() == want
+        assert s_sc.tolist() == [0.5 * (100 - j) for j in want]
