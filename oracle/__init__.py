@@ -93,6 +93,8 @@ def _sig(L):
     L.gbo_bf16_truncate.argtypes = [F32, C.c_int64, F32]
     L.gbo_sparse_vector.restype = C.c_int32
     L.gbo_sparse_vector.argtypes = [I32, C.c_int32, F32, C.c_int32, C.c_uint32, _p(np.uint32), F32]
+    L.gbo_als_observed_loss.restype = C.c_double
+    L.gbo_als_observed_loss.argtypes = [F32, F32, C.c_int32, C.c_int32, I64, I32, C.c_double, C.c_int32]
     U32 = _p(np.uint32)
     L.gbo_sparse_dot.restype = C.c_float
     L.gbo_sparse_dot.argtypes = [U32, F32, C.c_int32, U32, F32, C.c_int32]
@@ -173,6 +175,13 @@ def als_epoch(P, Q, user_off, user_items, item_off, item_users, reg, alpha):
 def als_epoch_threads(P, Q, user_off, user_items, item_off, item_users, reg, alpha, n_threads):
     return lib().gbo_als_epoch_threads(P, Q, P.shape[0], Q.shape[0], P.shape[1], i64(user_off), i32(user_items),
                                        i64(item_off), i32(item_users), reg, alpha, n_threads)
+
+
+def als_observed_loss(P, Q, user_off, user_items, w, n_threads=0):
+    """sum over observed (u,i) of (1 - p.q)^2 - w (p.q)^2 in double (test helper for the eALS objective)."""
+    import os
+    n_threads = n_threads or len(os.sched_getaffinity(0))
+    return lib().gbo_als_observed_loss(f32(P), f32(Q), P.shape[0], P.shape[1], i64(user_off), i32(user_items), float(w), n_threads)
 
 
 def bruteforce_search(X, q, k, prune0=False, metric=METRIC_NEG_DOT, self_index=-1):

@@ -765,6 +765,44 @@ double gbo_bruteforce_all(const float *X, int64_t N, int32_t d, int64_t q0, int6
     return t1 - t0;
 }
 
+/* Test helper, not a reference function: sum over observed (u,i) of (1 - r)^2 - w r^2 with r = p_u . q_i, the data
+ * part of the objective one eALS epoch (model.go:641-738) cannot increase; accumulated in double, rows over threads.
+ * tests/als_checks.py adds the Gram and regularisation terms. */
+typedef struct { const float *P, *Q; int32_t d; const int64_t *off; const int32_t *items; double w; int32_t u0, u1; double out; } obj_job;
+static void *obj_worker(void *arg)
+{
+    obj_job *jb = (obj_job *)arg;
+    double acc = 0.0;
+    for (int32_t u = jb->u0; u < jb->u1; u++) {
+        const float *p = jb->P + (int64_t)u * jb->d;
+        for (int64_t t = jb->off[u]; t < jb->off[u + 1]; t++) {
+            const float *q = jb->Q + (int64_t)jb->items[t] * jb->d;
+            double r = 0.0;
+            for (int32_t k = 0; k < jb->d; k++) r += (double)p[k] * (double)q[k];
+            acc += (1.0 - r) * (1.0 - r) - jb->w * r * r;
+        }
+    }
+    jb->out = acc;
+    return NULL;
+}
+double gbo_als_observed_loss(const float *P, const float *Q, int32_t n_users, int32_t d, const int64_t *user_off,
+                             const int32_t *user_items, double w, int32_t n_threads)
+{
+    if (n_threads < 1) n_threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    obj_job *jobs = (obj_job *)malloc(sizeof(obj_job) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; t++) {
+        obj_job jb = {P, Q, d, user_off, user_items, w, (int32_t)((int64_t)n_users * t / n_threads),
+                      (int32_t)((int64_t)n_users * (t + 1) / n_threads), 0.0};
+        jobs[t] = jb;
+        pthread_create(&th[t], NULL, obj_worker, &jobs[t]);
+    }
+    double tot = 0.0;
+    for (int t = 0; t < n_threads; t++) { pthread_join(th[t], NULL); tot += jobs[t].out; }
+    free(th); free(jobs);
+    return tot;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Similarity vectors and scores: logics/item_to_item.go, logics/user_to_user.go, logics/vector_writer.go
  * ---------------------------------------------------------------------------------------- */

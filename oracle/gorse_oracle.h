@@ -91,6 +91,9 @@ double gbo_bruteforce_all(const float *X, int64_t N, int32_t d, int64_t q0, int6
                           int32_t *out_idx, float *out_score, int32_t *out_count);
 
 /* ---- model/cf/evaluator.go ---- */
+/* test helper: data part of the eALS objective (see tests/als_checks.py) */
+double gbo_als_observed_loss(const float *P, const float *Q, int32_t n_users, int32_t d, const int64_t *user_off,
+                             const int32_t *user_items, double w, int32_t n_threads);
 /* logics: similarity vectors and scores (item_to_item.go, user_to_user.go, vector_writer.go) */
 void gbo_bf16_truncate(const float *in, int64_t n, float *out);                                    /* bfloats.go:23-37 */
 int32_t gbo_sparse_vector(const int32_t *ids, int32_t n_ids, const float *idf, int32_t n_idf, uint32_t offset,

@@ -60,3 +60,29 @@ def test_oracle_als_epoch_matches_line_by_line_transcription(orc):
             als_epoch_py(orc, P, Q, user_fb, item_fb, 0.06, 0.001)
             orc.als_epoch(Po, Qo, off, items, ioff, iusers, 0.06, 0.001)
             assert P.tobytes() == Po.tobytes() and Q.tobytes() == Qo.tobytes()
+
+
+def test_objective_is_monotone_and_reduced_problem_reproduces_rows(orc):
+    """Validates, on the oracle, the two checks the full-size GPU test (tests/test_fullsize_gpu.py, C3) relies on."""
+    import gorse_b200 as gb
+    from gorse_b200 import synth
+
+    from als_checks import als_objective, oracle_user_rows
+
+    U, I, d = 500, 180, 32
+    off, items = synth.make_feedback(U, I, 6000, seed=4, zipf_s=1.2)
+    assert (np.bincount(items, minlength=I) == 0).any()          # some items without feedback, as at C3
+    ioff, iusers = gb.transpose_csr(off, items, I)
+    rng = np.random.default_rng(1)
+    P = (rng.standard_normal((U, d)) * 0.1).astype(np.float32)
+    Q = (rng.standard_normal((I, d)) * 0.1).astype(np.float32)
+    P0, Q0 = P.copy(), Q.copy()
+    losses = [als_objective(orc, P, Q, off, items, 0.001, 0.06)]
+    for ep in range(3):
+        orc.als_epoch(P, Q, off, items, ioff, iusers, 0.06, 0.001)
+        losses.append(als_objective(orc, P, Q, off, items, 0.001, 0.06))
+        if ep == 0:
+            users = np.array([0, 7, 123, 499, int(np.diff(off).argmax())])
+            rows = oracle_user_rows(orc, gb.transpose_csr, P0, Q0, off, items, users, 0.06, 0.001)
+            assert rows.tobytes() == P[users].tobytes()
+    assert all(b < a for a, b in zip(losses, losses[1:])), losses
