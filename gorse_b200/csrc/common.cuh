@@ -99,9 +99,9 @@ struct DevBuf {
     int32_t alloc(size_t count)
     {
         free();
-        n = count;
         if (count == 0) return GORSE_B200_OK;
         GB_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        n = count;   // only a successful allocation has a size
         return GORSE_B200_OK;
     }
     void free()
