@@ -34,18 +34,71 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
+// Two fp32 FMAs per instruction (Blackwell FFMA2, PTX fma.rn.f32x2): both halves are ordinary IEEE fp32 FMAs.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
+{
+    return ((unsigned long long)__float_as_uint(hi) << 32) | (unsigned long long)__float_as_uint(lo);
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+// acc[x][y] += a[x] * b[y] over a TxT register tile; F2 pairs the y direction (T even)
+template <int T, bool F2>
+struct GramTile {
+    float acc[T][T];
+    unsigned long long acc2[T][F2 ? T / 2 : 1];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int x = 0; x < T; x++) {
+#pragma unroll
+            for (int y = 0; y < T; y++) acc[x][y] = 0.f;
+#pragma unroll
+            for (int y = 0; y < (F2 ? T / 2 : 1); y++) acc2[x][y] = 0ull;
+        }
+    }
+    __device__ __forceinline__ void mac(const float (&a)[T], const float (&b)[T])
+    {
+        if constexpr (F2) {
+            unsigned long long b2[T / 2];
+#pragma unroll
+            for (int y = 0; y < T / 2; y++) b2[y] = pack2(b[2 * y], b[2 * y + 1]);
+#pragma unroll
+            for (int x = 0; x < T; x++) {
+                const unsigned long long ax = pack2(a[x], a[x]);
+#pragma unroll
+                for (int y = 0; y < T / 2; y++) acc2[x][y] = ffma2(ax, b2[y], acc2[x][y]);
+            }
+        } else {
+#pragma unroll
+            for (int x = 0; x < T; x++)
+#pragma unroll
+                for (int y = 0; y < T; y++) acc[x][y] = __fmaf_rn(a[x], b[y], acc[x][y]);
+        }
+    }
+    __device__ __forceinline__ float get(int x, int y) const
+    {
+        if constexpr (F2) {
+            const unsigned long long v = acc2[x][y >> 1];
+            return __uint_as_float((unsigned)((y & 1) ? (v >> 32) : v));
+        } else {
+            return acc[x][y];
+        }
+    }
+};
+
 // Partial Gram of rows [r0, r1) handled by this CTA; TxT register tile per thread, 16x16 threads.
-template <int T>
+template <int T, bool F2>
 __global__ void __launch_bounds__(256) gram_kernel(const float *X, int32_t rows, int d, const int64_t *off, float *partial)
 {
     extern __shared__ float xs[];  // [16][dp]
     const int dp = 16 * T;         // padded width
     const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
-    float acc[T][T];
-#pragma unroll
-    for (int a = 0; a < T; a++)
-#pragma unroll
-        for (int b = 0; b < T; b++) acc[a][b] = 0.f;
+    GramTile<T, F2> tile;
+    tile.zero();
     int64_t per = ((int64_t)rows + gridDim.x - 1) / gridDim.x;
     int64_t r0 = (int64_t)blockIdx.x * per, r1 = min((int64_t)rows, r0 + per);
     for (int64_t base = r0; base < r1; base += 16) {
@@ -63,10 +116,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float *X, int32_t rows,
             float a[T], b[T];
 #pragma unroll
             for (int k = 0; k < T; k++) { a[k] = xs[rr * dp + ti * T + k]; b[k] = xs[rr * dp + tj * T + k]; }
-#pragma unroll
-            for (int x = 0; x < T; x++)
-#pragma unroll
-                for (int y = 0; y < T; y++) acc[x][y] = __fmaf_rn(a[x], b[y], acc[x][y]);
+            tile.mac(a, b);
         }
         __syncthreads();
     }
@@ -76,7 +126,7 @@ __global__ void __launch_bounds__(256) gram_kernel(const float *X, int32_t rows,
 #pragma unroll
         for (int y = 0; y < T; y++) {
             int i = ti * T + x, j = tj * T + y;
-            if (i < d && j < d) out[i * d + j] = acc[x][y];
+            if (i < d && j < d) out[i * d + j] = tile.get(x, y);
         }
 }
 
@@ -392,20 +442,18 @@ als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_
 // same 16x16-thread register tiling as gram_kernel, and one CTA per row sums the partials and does the sweep.
 #define GB_ALS_CHUNK 2048
 
-template <int T>
+template <int T, bool F2>
 __global__ void __launch_bounds__(256) als_chunk_gram_kernel(const float *Y, int d, const int32_t *idx, const int32_t *chunk_row,
                                                              const int64_t *chunk_begin, const int32_t *chunk_len, float *partial)
 {
     extern __shared__ float xs[];  // [16][dp]
     const int dp = 16 * T;
     const int ti = threadIdx.x >> 4, tj = threadIdx.x & 15;
-    float acc[T][T], hacc[T];
+    GramTile<T, F2> tile;
+    tile.zero();
+    float hacc[T];
 #pragma unroll
-    for (int a = 0; a < T; a++) {
-        hacc[a] = 0.f;
-#pragma unroll
-        for (int b = 0; b < T; b++) acc[a][b] = 0.f;
-    }
+    for (int a = 0; a < T; a++) hacc[a] = 0.f;
     const int64_t b0 = chunk_begin[blockIdx.x];
     const int len = chunk_len[blockIdx.x];
     for (int base = 0; base < len; base += 16) {
@@ -421,10 +469,7 @@ __global__ void __launch_bounds__(256) als_chunk_gram_kernel(const float *Y, int
             float a[T], b[T];
 #pragma unroll
             for (int k = 0; k < T; k++) { a[k] = xs[rr * dp + ti * T + k]; b[k] = xs[rr * dp + tj * T + k]; }
-#pragma unroll
-            for (int x = 0; x < T; x++)
-#pragma unroll
-                for (int y = 0; y < T; y++) acc[x][y] = __fmaf_rn(a[x], b[y], acc[x][y]);
+            tile.mac(a, b);
             if (ti == 0) {
 #pragma unroll
                 for (int y = 0; y < T; y++) hacc[y] += b[y];
@@ -438,7 +483,7 @@ __global__ void __launch_bounds__(256) als_chunk_gram_kernel(const float *Y, int
 #pragma unroll
         for (int y = 0; y < T; y++) {
             int i = ti * T + x, j = tj * T + y;
-            if (i < d && j < d) out[i * d + j] = acc[x][y];
+            if (i < d && j < d) out[i * d + j] = tile.get(x, y);
         }
     if (ti == 0) {
 #pragma unroll
@@ -489,6 +534,14 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
     }
 }
 
+// GORSE_B200_ALS_FMA2=1: the Gram register tiles issue FFMA2 (two fp32 FMAs per instruction; the scalar FFMA issues at
+// half the fp32 peak on Blackwell).  Off by default until measured and parity-checked on the GPU (experiment queue).
+static bool als_fma2()
+{
+    static bool f = [] { const char *e = getenv("GORSE_B200_ALS_FMA2"); return e && atoi(e) == 1; }();
+    return f;
+}
+
 static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const int64_t *off)
 {
     gorse_b200_ctx *c = cf->ctx;
@@ -499,11 +552,18 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
     if (d <= 128) {
         int T = d <= 16 ? 1 : d <= 32 ? 2 : d <= 64 ? 4 : 8;
         size_t sm = sizeof(float) * 16 * 16 * T;
+        const bool f2 = als_fma2();
         switch (T) {
-            case 1: gram_kernel<1><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
-            case 2: gram_kernel<2><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
-            case 4: gram_kernel<4><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
-            default: gram_kernel<8><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            case 1: gram_kernel<1, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            case 2: if (f2) gram_kernel<2, true><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
+                    else gram_kernel<2, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
+                    break;
+            case 4: if (f2) gram_kernel<4, true><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
+                    else gram_kernel<4, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
+                    break;
+            default: if (f2) gram_kernel<8, true><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
+                     else gram_kernel<8, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
+                     break;
         }
     } else {
         gram_generic_kernel<<<parts, 256, 0, c->stream>>>(X, rows, d, off, cf->scratch.p);
@@ -665,12 +725,15 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             const int d = cf->d, T = d <= 16 ? 1 : d <= 32 ? 2 : d <= 64 ? 4 : 8;
             const size_t gsm = sizeof(float) * 16 * 16 * T;
             const int nc = cf->als_n_chunks[side];
+            auto *ck = als_chunk_gram_kernel<1, false>;
+            const bool f2 = als_fma2();
             switch (T) {
-                case 1: als_chunk_gram_kernel<1><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
-                case 2: als_chunk_gram_kernel<2><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
-                case 4: als_chunk_gram_kernel<4><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
-                default: als_chunk_gram_kernel<8><<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p); break;
+                case 1: break;
+                case 2: ck = f2 ? als_chunk_gram_kernel<2, true> : als_chunk_gram_kernel<2, false>; break;
+                case 4: ck = f2 ? als_chunk_gram_kernel<4, true> : als_chunk_gram_kernel<4, false>; break;
+                default: ck = f2 ? als_chunk_gram_kernel<8, true> : als_chunk_gram_kernel<8, false>; break;
             }
+            ck<<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p);
             GB_LAUNCHED(c);
             const size_t ssm = sizeof(float) * ((size_t)d * (d + 1) + 2 * d);
             als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, rows, cf->als_row_chunk0[side].p, cf->als_partial.p);

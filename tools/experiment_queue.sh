@@ -1,0 +1,27 @@
+#!/bin/bash
+# Experiments that were written without GPU time left (end of round 1), all OFF by default.  One gpurun call runs the
+# parity tests and the bench under each switch so that the next round can flip (or delete) them on evidence:
+#   /usr/local/graft/bin/gpurun --timeout 500 -- 'bash tools/experiment_queue.sh'
+#   GORSE_B200_ALS_FMA2=1   Gram register tiles issue FFMA2 (2 fp32 FMAs / instruction): gram_kernel, als_chunk_gram_kernel
+#   GORSE_B200_TOPK_EPI8=1  stage-1 epilogue tests 8 columns per branch with a 3-input max tree (FMNMX3)
+#   GORSE_B200_ALS_BLOCK=4  four coordinates per shuffle butterfly (measured slower in round 1; kept for reference)
+#   GORSE_B200_ALS_G16=0    whole-warp classes for 9..32-entry rows (measured slower in round 1)
+O=gpurun_out/experiments
+mkdir -p $O
+line() { python - "$1" <<'PY'
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], "ms/step", round(d["ms_per_step"], 3), "value", f'{d["value"]:.4g}', "frac", round(d["roofline"]["frac"], 4))
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+}
+echo "== FMA2: ALS parity + C3 bench (baseline first)"
+timeout 90 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/c3_base.json 2> $O/c3.err; line $O/c3_base.json
+GORSE_B200_ALS_FMA2=1 timeout 90 python -m pytest tests/test_als_gpu.py -x -q 2>&1 | tail -2
+GORSE_B200_ALS_FMA2=1 timeout 90 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu > $O/c3_fma2.json 2>> $O/c3.err; line $O/c3_fma2.json
+echo "== EPI8: top-k parity + C4 bench (baseline first)"
+timeout 150 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu > $O/c4_base.json 2> $O/c4.err; line $O/c4_base.json
+GORSE_B200_TOPK_EPI8=1 timeout 150 python -m pytest tests/test_topk_mma_gpu.py tests/test_topk_gpu.py tests/test_logics_gpu.py -x -q 2>&1 | tail -2
+GORSE_B200_TOPK_EPI8=1 timeout 150 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu > $O/c4_epi8.json 2>> $O/c4.err; line $O/c4_epi8.json
