@@ -595,6 +595,15 @@ static const GroupClass *group_classes()
 
 static bool als_grouped(const gorse_b200_cf *cf) { return cf->d % 32 == 0 && cf->d <= 128; }
 
+// rows of `side` (0 users, 1 items) this rank updates: users as in cf_create (cf->u_lo/u_hi), items by the same rule
+static void shard_range(const gorse_b200_cf *cf, int side, int32_t &lo, int32_t &hi)
+{
+    const gorse_b200_ctx *c = cf->ctx;
+    const int32_t rows = side == 0 ? cf->n_users : cf->n_items;
+    lo = (int32_t)((int64_t)rows * c->rank / c->world);
+    hi = (int32_t)((int64_t)rows * (c->rank + 1) / c->world);
+}
+
 static int32_t prepare_als(gorse_b200_cf *cf)
 {
     if (cf->als_ready) return GORSE_B200_OK;
@@ -604,7 +613,10 @@ static int32_t prepare_als(gorse_b200_cf *cf)
         const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
         int32_t rows = side == 0 ? cf->n_users : cf->n_items;
         std::vector<int32_t> cls[5];
-        for (int32_t r = 0; r < rows; r++) {
+        // multi-rank: this rank updates its own range of users and of items only
+        int32_t r_lo = 0, r_hi = rows;
+        shard_range(cf, side, r_lo, r_hi);
+        for (int32_t r = r_lo; r < r_hi; r++) {
             int64_t n = off[(size_t)r + 1] - off[r];
             int k;
             if (grouped) {
@@ -764,26 +776,71 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
 
 using namespace gb;
 
+// every rank sends its own row range of `table` (rows x d, present in full on every rank) to all the others
+static int32_t exchange_shards(gorse_b200_cf *cf, int side, float *table)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    GB_NCCL_API(nc);
+    if (!nc->Broadcast || !nc->GroupStart || !nc->GroupEnd) {
+        set_error("the loaded libnccl lacks ncclBroadcast/ncclGroupStart/ncclGroupEnd");
+        return GORSE_B200_ERR_NCCL;
+    }
+    const int64_t rows = side == 0 ? cf->n_users : cf->n_items;
+    GB_NCCL(nc, GroupStart());
+    for (int r = 0; r < c->world; r++) {
+        const int64_t lo = rows * r / c->world, hi = rows * (r + 1) / c->world;
+        if (hi == lo) continue;
+        float *p = table + lo * cf->d;
+        GB_NCCL(nc, Broadcast(p, p, (size_t)(hi - lo) * cf->d, ncclFloat32, r, c->comm, c->stream));
+    }
+    GB_NCCL(nc, GroupEnd());
+    return GORSE_B200_OK;
+}
+
 extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alpha)
 {
     GB_CHECK_ARG(cf != nullptr, "cf is NULL");
     if (!cf->has_item_csr) { set_error("als_epoch needs the item CSR (item_off/item_users) at cf_create"); return GORSE_B200_ERR_STATE; }
-    if (cf->ctx->world != 1) { set_error("als_epoch is single-GPU in this round (world must be 1)"); return GORSE_B200_ERR_UNSUPPORTED; }
     ScopedDevice sd(cf->ctx->device);
+    gorse_b200_ctx *c = cf->ctx;
+    const bool multi = c->world > 1;
     GB_TRY(prepare_als(cf));
     DevBuf<float> pred;
     GB_TRY(pred.alloc((size_t)std::max<int64_t>(1, cf->n_feedback)));
     int32_t st;
     auto done = [&](int32_t s) {
-        cudaStreamSynchronize(cf->ctx->stream);
+        cudaStreamSynchronize(c->stream);
         pred.free();
         return s;
     };
+    // Multi-rank: Q is replicated and P is range-sharded as for BPR.  The user half-sweep needs only Q, the item
+    // half-sweep needs ALL of P, so the epoch works on a full copy P_all: own rows in, user sweep on the own range, ranges
+    // exchanged, S^p and the item sweep (own item range) on P_all, item ranges of Q exchanged, own rows of P_all back.
+    // Both Grams are computed in full on every rank from replicated data, so every rank holds bit-identical S^q, S^p, Q.
+    float *P = cf->P.p;
+    const int64_t own = (int64_t)(cf->u_hi - cf->u_lo) * cf->d;
+    if (multi) {
+        if (cf->P_all.n == 0 && (st = cf->P_all.alloc((size_t)cf->n_users * cf->d))) return done(st);
+        P = cf->P_all.p;
+        if (own) {
+            cudaError_t e = cudaMemcpyAsync(P + (int64_t)cf->u_lo * cf->d, cf->P.p, own * sizeof(float), cudaMemcpyDeviceToDevice, c->stream);
+            if (e != cudaSuccess) { set_error("als_epoch: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+        }
+    }
     if ((st = run_gram(cf, cf->Q.p, cf->n_items, cf->item_off.p))) return done(st);
-    if ((st = run_rows(cf, 0, cf->P.p, cf->Q.p, cf->user_off.p, cf->user_items.p, reg, alpha, pred.p))) return done(st);
-    if ((st = run_gram(cf, cf->P.p, cf->n_users, cf->user_off.p))) return done(st);
-    if ((st = run_rows(cf, 1, cf->Q.p, cf->P.p, cf->item_off.p, cf->item_users.p, reg, alpha, pred.p))) return done(st);
-    cudaError_t e = cudaStreamSynchronize(cf->ctx->stream);
+    if ((st = run_rows(cf, 0, P, cf->Q.p, cf->user_off.p, cf->user_items.p, reg, alpha, pred.p))) return done(st);
+    if (multi && (st = exchange_shards(cf, 0, P))) return done(st);
+    if ((st = run_gram(cf, P, cf->n_users, cf->user_off.p))) return done(st);
+    if ((st = run_rows(cf, 1, cf->Q.p, P, cf->item_off.p, cf->item_users.p, reg, alpha, pred.p))) return done(st);
+    if (multi) {
+        if ((st = exchange_shards(cf, 1, cf->Q.p))) return done(st);
+        cudaError_t e = cudaSuccess;
+        if (own) e = cudaMemcpyAsync(cf->P.p, P + (int64_t)cf->u_lo * cf->d, own * sizeof(float), cudaMemcpyDeviceToDevice, c->stream);
+        // the BPR exchange keeps the last synchronised item table in Q0
+        if (e == cudaSuccess && cf->Q0.n) e = cudaMemcpyAsync(cf->Q0.p, cf->Q.p, cf->Q.n * sizeof(float), cudaMemcpyDeviceToDevice, c->stream);
+        if (e != cudaSuccess) { set_error("als_epoch: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) { set_error("als_epoch: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
     return done(GORSE_B200_OK);
 }

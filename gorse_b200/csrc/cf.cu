@@ -234,7 +234,7 @@ int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
     if (!cf) return GORSE_B200_OK;
     ScopedDevice sd(cf->ctx->device);
     cudaStreamSynchronize(cf->ctx->stream);
-    cf->P.free(); cf->Q.free(); cf->Q0.free(); cf->item_rate.free(); cf->xchg.free();
+    cf->P.free(); cf->Q.free(); cf->Q0.free(); cf->item_rate.free(); cf->xchg.free(); cf->P_all.free();
     cf->user_off.free(); cf->item_off.free();
     cf->user_items.free(); cf->item_users.free(); cf->active.free(); cf->user_meta.free();
     cf->hot_items.free(); cf->hot_slot.free(); cf->hot.free(); cf->hotq.free(); cf->hot_sorted.free(); cf->hot_ctr.free();

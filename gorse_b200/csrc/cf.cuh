@@ -40,6 +40,7 @@ struct gorse_b200_cf {
     gb::DevBuf<float> P, Q, Q0;
     // multi-rank item exchange (bpr.cu): expected updates of item i per local BPR step, and the [a | L | psq] buffer
     gb::DevBuf<float> item_rate, xchg;
+    gb::DevBuf<float> P_all;   // multi-rank eALS: the full user table (every rank needs all of P for its item rows)
     gb::DevBuf<int64_t> user_off, item_off;
     gb::DevBuf<int32_t> user_items, item_users, active;
     gb::DevBuf<gb::UserMeta> user_meta;

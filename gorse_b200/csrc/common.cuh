@@ -45,6 +45,10 @@ struct NcclApi {
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
     ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
     const char *(*GetErrorString)(ncclResult_t);
+    // optional (only the multi-rank eALS epoch uses them; nullptr when the loaded libnccl lacks them)
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
 };
 const NcclApi *nccl();  // nullptr (and last_error set) when libnccl cannot be loaded
 

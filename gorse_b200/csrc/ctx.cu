@@ -41,6 +41,9 @@ const NcclApi *nccl()
     api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
     api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    api.Broadcast = (decltype(api.Broadcast))dlsym(h, "ncclBroadcast");
+    api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
     if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllReduce || !api.AllGather || !api.GetErrorString) {
         set_error("libnccl is missing a required symbol");
         return nullptr;
