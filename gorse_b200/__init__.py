@@ -294,6 +294,48 @@ class BruteforceIndex:
         self.close()
 
 
+class SparseIndex:
+    """EXPERIMENTAL (not yet run on hardware): brute-force Dot search over sparse vectors, the store side of the
+    tags / users / auto similarity types (storage/vectors/xvec.go:244-248)."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        h = C.c_void_p()
+        check(lib.gorse_b200_sparse_index_create(ctx.h, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib.gorse_b200_sparse_index_destroy(self.h)
+            self.h = None
+
+    def add(self, off, indices, values):
+        """CSR batch: off int64 [n+1] from 0, indices uint32 strictly ascending per vector, values float32."""
+        off = np.ascontiguousarray(off, np.int64)
+        indices = np.ascontiguousarray(indices, np.uint32)
+        values = np.ascontiguousarray(values, np.float32)
+        n = C.c_int64(0)
+        check(lib.gorse_b200_sparse_index_add(self.h, ptr(off), ptr(indices), ptr(values), len(off) - 1, C.byref(n)))
+        return n.value
+
+    def __len__(self):
+        n = C.c_int64(0)
+        check(lib.gorse_b200_sparse_index_len(self.h, C.byref(n)))
+        return n.value
+
+    def search_range(self, q0, q1, k):
+        nq = max(q1 - q0, 0)
+        idx, dot, cnt = np.full((nq, k), -1, np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
+        check(lib.gorse_b200_sparse_index_search_range(self.h, q0, q1, k, ptr(idx), ptr(dot), ptr(cnt)))
+        return idx, dot, cnt
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 # ---- logics: similarity vectors and scores (host functions; SURVEY 8a row J) ---------------------------------
 def bf16_truncate(a):
     """bfloats.FromFloat32 + ToFloat32 (common/bfloats/bfloats.go:23-37): how the reference stores dense embeddings."""

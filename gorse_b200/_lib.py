@@ -72,6 +72,11 @@ PROTOTYPES = {
     "gorse_b200_similar_scores": (C.c_int32, [C.c_int32, C.c_double, C.c_int32, C.c_int32, VP, VP, C.c_int32, VP, VP,
                                               C.POINTER(C.c_int32)]),
     "gorse_b200_index_query_similar": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int32, C.c_double, VP, VP, VP]),
+    "gorse_b200_sparse_index_create": (C.c_int32, [VP, PVP]),
+    "gorse_b200_sparse_index_destroy": (C.c_int32, [VP]),
+    "gorse_b200_sparse_index_add": (C.c_int32, [VP, VP, VP, VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "gorse_b200_sparse_index_len": (C.c_int32, [VP, C.POINTER(C.c_int64)]),
+    "gorse_b200_sparse_index_search_range": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int32, VP, VP, VP]),
 }
 
 

@@ -251,6 +251,25 @@ int32_t gorse_b200_similar_scores(int32_t metric, double score_scale, int32_t se
 int32_t gorse_b200_index_query_similar(gorse_b200_index *ix, int64_t q0, int64_t q1, int32_t n, double score_scale,
                                        int32_t *ids_out, double *scores_out, int32_t *count_out);
 
+/* ------------------------------------------------------------------------------------------
+ * EXPERIMENTAL (compiled, not yet run on hardware): brute-force search over sparse
+ * vectors with the Dot metric -- what the "tags" / "users" / "auto" similarity types ask their vector
+ * store for (storage/vectors/xvec.go:244-248 flat sparse index, :405 query).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gorse_b200_sparse_index gorse_b200_sparse_index;
+int32_t gorse_b200_sparse_index_create(gorse_b200_ctx *ctx, gorse_b200_sparse_index **out);
+int32_t gorse_b200_sparse_index_destroy(gorse_b200_sparse_index *ix);
+/* append n vectors given as CSR (off[n+1] with off[0] = 0; indices strictly ascending inside a vector,
+ * as appendSparseVector produces them from sorted ids); *count_out = number of vectors afterwards */
+int32_t gorse_b200_sparse_index_add(gorse_b200_sparse_index *ix, const int64_t *off, const uint32_t *indices, const float *values,
+                                    int64_t n, int64_t *count_out);
+int32_t gorse_b200_sparse_index_len(const gorse_b200_sparse_index *ix, int64_t *count_out);
+/* the k (<= 128) stored vectors with the largest POSITIVE dot with each stored vector in [q0, q1), the vector
+ * itself excluded; best first (ties: lower index first); idx_out/dot_out are (q1-q0) x k padded with -1 / 0.
+ * Feed a row to gorse_b200_similar_scores with GORSE_B200_METRIC_NEG_DOT after negating the dots. */
+int32_t gorse_b200_sparse_index_search_range(gorse_b200_sparse_index *ix, int64_t q0, int64_t q1, int32_t k, int32_t *idx_out,
+                                             float *dot_out, int32_t *count_out);
+
 #ifdef __cplusplus
 }
 #endif
