@@ -25,3 +25,6 @@ echo "== EPI8: top-k parity + C4 bench (baseline first)"
 timeout 150 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu > $O/c4_base.json 2> $O/c4.err; line $O/c4_base.json
 GORSE_B200_TOPK_EPI8=1 timeout 150 python -m pytest tests/test_topk_mma_gpu.py tests/test_topk_gpu.py tests/test_logics_gpu.py -x -q 2>&1 | tail -2
 GORSE_B200_TOPK_EPI8=1 timeout 150 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu > $O/c4_epi8.json 2>> $O/c4.err; line $O/c4_epi8.json
+echo "== experimental sparse Dot index (csrc/sparse.cu): parity vs the oracle + reference known answers"
+GORSE_B200_EXPERIMENTAL=1 timeout 120 python -m pytest tests/test_sparse_gpu.py -x -q 2>&1 | tail -3
+# separately, on two GPUs:  gpurun --gpus 2 -- 'python -m pytest tests/test_dist_gpu.py -x -q'   (BPR exchange + the multi-rank eALS epoch)
