@@ -235,7 +235,10 @@ __device__ __forceinline__ float *item_ref(const BprView &v, int32_t it, int32_t
 // same addresses (one coalesced request per piece), sum their 8 row deltas with shuffles and issue ONE red per piece:
 // 8x fewer operations on the row's L2 atomic units, which otherwise bound the top item (measured: 16 loads + 16 reds
 // per triple on one striped row sustain only ~2*10^8 updates/s).
-template <int C>
+// PF (experiment queue, GORSE_B200_HOT_PREFETCH=1): the user row of the entry two rounds ahead is prefetched into L2 as
+// soon as its index has arrived, so that next round's gather (issued one round before use) is an L2 hit instead of an
+// HBM access -- the user table (256 MB at C2) is the only operand of this kernel that does not live in L2.
+template <int C, bool PF>
 __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot, const unsigned *begin, const unsigned *first_quad,
                                                             const int32_t *sorted, float lr, float reg)
 {
@@ -310,6 +313,13 @@ __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot
                 dq[c].z += __shfl_xor_sync(0xffffffffu, dq[c].z, sft); dq[c].w += __shfl_xor_sync(0xffffffffu, dq[c].w, sft);
             }
             if (lane < 4) red_row(Qh + sh * c, dq[c]);
+        }
+        if constexpr (PF) {
+            if (u3 >= 0) {
+                const float *pp = v.P + (int64_t)(u3 - v.u_lo) * v.d + 4 * lane4;
+#pragma unroll
+                for (int c = 0; c < C; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16 * c));
+            }
         }
 #pragma unroll
         for (int c = 0; c < C; c++) { r.p[c] = rn.p[c]; r.qj[c] = rn.qj[c]; }
@@ -723,12 +733,15 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
             hot_fill_kernel<<<sg, 256, nh * sizeof(unsigned), c->stream>>>(hq, nh, cursor, cf->hot_sorted.p);
             GB_LAUNCHED(c);
             const int hg = (int)((quad_budget + (unsigned)nh + 63u) / 64u);  // upper bound of quads in use; the rest exit
+            static const bool pf = [] { const char *e = getenv("GORSE_B200_HOT_PREFETCH"); return e && atoi(e) == 1; }();
+            auto *hk = bpr_hot_apply_kernel<1, false>;
             switch (C) {
-                case 1: bpr_hot_apply_kernel<1><<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg); break;
-                case 2: bpr_hot_apply_kernel<2><<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg); break;
-                case 4: bpr_hot_apply_kernel<4><<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg); break;
-                default: bpr_hot_apply_kernel<8><<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg); break;
+                case 1: hk = pf ? bpr_hot_apply_kernel<1, true> : bpr_hot_apply_kernel<1, false>; break;
+                case 2: hk = pf ? bpr_hot_apply_kernel<2, true> : bpr_hot_apply_kernel<2, false>; break;
+                case 4: hk = pf ? bpr_hot_apply_kernel<4, true> : bpr_hot_apply_kernel<4, false>; break;
+                default: hk = pf ? bpr_hot_apply_kernel<8, true> : bpr_hot_apply_kernel<8, false>; break;
             }
+            hk<<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg);
             GB_LAUNCHED(c);
             hot_scatter_kernel<<<div_up((int64_t)cf->n_hot * (cf->d / 4), 256), 256, 0, c->stream>>>(cf->Q.p, cf->d, cf->hot_items.p, cf->n_hot, cf->hot_pad, cf->hot.p);
             GB_LAUNCHED(c);
