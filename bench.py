@@ -281,6 +281,7 @@ def run_ours(args):
         if not all_ok:
             e2e_error = e2e_error or "another rank could not allocate its pinned mirror"
     if not args.no_e2e and e2e_error is None:
+        m2 = None
         try:
             rng = np.random.default_rng(1)
             hp.array[:] = (rng.standard_normal((upr, d)) * INIT_STD).astype(np.float32)
@@ -312,11 +313,13 @@ def run_ours(args):
                    "what": f"one Fit-shaped call per rank: cf_create (CSR upload) + set_factors from the pinned mirror + {e_epochs} epochs "
                            f"(reference default NEpochs) + get_factors; bytes are per rank and per epoch, amortised over the call",
                    "wall_s": e_sec}
-            m2.close()
-            hp.free()
-            hq.free()
         except Exception as ex:  # keep the contract line even if the end-to-end leg fails
             e2e_error = f"{type(ex).__name__}: {ex}"
+        finally:
+            if m2 is not None:
+                m2.close()
+            hp.free()
+            hq.free()
     if model is not None:
         model.close()
 
