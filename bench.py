@@ -280,6 +280,9 @@ def run_ours(args):
         all_ok = -max_over_ranks(-1.0 if (hp is not None and hq is not None) else 0.0) > 0.5
         if not all_ok:
             e2e_error = e2e_error or "another rank could not allocate its pinned mirror"
+            for buf in (hp, hq):
+                if buf is not None:
+                    buf.free()
     if not args.no_e2e and e2e_error is None:
         m2 = None
         try:
