@@ -484,7 +484,7 @@ def run_topk(args):
                       "gpu_launches": int(launches), "clocks": clocks}), flush=True)
 
 
-def main():
+def build_parser():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -498,7 +498,11 @@ def main():
     ap.add_argument("--zipf", type=float, default=None, help="item popularity exponent of the synthetic data (default 1.0; 0 = uniform)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    args = ap.parse_args()
+    return ap
+
+
+def main():
+    args = build_parser().parse_args()
     if args.zipf is not None:
         global ZIPF_S
         ZIPF_S = args.zipf
