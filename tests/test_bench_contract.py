@@ -71,6 +71,9 @@ class _FakePinned:
 
 
 def _fake_gb(real):
+    import importlib
+
+    synth = importlib.import_module(real.__name__ + ".synth")
     m = types.ModuleType("gorse_b200")
     for k in dir(real):
         if not k.startswith("__"):
@@ -79,7 +82,7 @@ def _fake_gb(real):
     m.check = lambda st: None
     m.ptr = lambda a: None
     m.lib = types.SimpleNamespace(gorse_b200_cf_set_factors=lambda *a: 0, gorse_b200_cf_get_factors=lambda *a: 0)
-    m.synth = real.synth
+    m.synth = synth
     return m
 
 
