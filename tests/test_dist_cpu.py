@@ -94,3 +94,37 @@ def test_bench_two_ranks_with_a_mocked_device(tmp_path):
                           "--master-port", "29534", str(script)], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert (tmp_path / "bench_ok_0").exists() and (tmp_path / "bench_ok_1").exists()
+
+
+TOPK_WORKER = r'''
+import os, sys, types, json, io, contextlib
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "tests"))
+import gorse_b200 as real
+import bench
+from test_bench_contract import _fake_gb, _FakeIndex
+fake = _fake_gb(real)
+fake.BruteforceIndex = _FakeIndex
+sys.modules["gorse_b200"] = fake
+bench.ClockSampler = lambda *a: types.SimpleNamespace(stop=lambda t0, t1: None)
+args = bench.build_parser().parse_args(["--workload", "c4", "--small", "--gpus", "2", "--queries", "1024", "--steps", "2", "--no-cpu"])
+buf = io.StringIO()
+with contextlib.redirect_stdout(buf):
+    bench.run_topk(args)
+rank = int(os.environ["RANK"])
+out = buf.getvalue().strip()
+if rank == 0:
+    line = json.loads(out.splitlines()[-1])
+    assert line["n_gpus"] == 2 and abs(line["value"] - 2 * 1024 / (line["ms_per_step"] * 1e-3)) < 1e-6 * line["value"], line
+else:
+    assert out == "", out
+open(os.path.join(%r, f"topk_ok_{rank}"), "w").write("ok")
+'''
+
+
+def test_bench_topk_two_ranks_with_a_mocked_device(tmp_path):
+    script = tmp_path / "topk_worker.py"
+    script.write_text(TOPK_WORKER % (ROOT, ROOT, str(tmp_path)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29535", str(script)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert (tmp_path / "topk_ok_0").exists() and (tmp_path / "topk_ok_1").exists()
