@@ -88,3 +88,21 @@ def test_synth_shapes(gb):
     assert no[-1] == 500 * 20
     t = synth.conflict_free_triples(off, items, 200, 40, seed=4)
     assert len(set(t[:, 0])) == len(t) and len(set(t[:, 1]) | set(t[:, 2])) == 2 * len(t)
+
+
+def test_go_shim_only_calls_declared_entry_points():
+    """The cgo shim cannot be compiled here (no Go toolchain); at least every C.gorse_b200_* / C.GORSE_B200_* it names must be
+    declared in include/gorse_b200.h."""
+    header = open(os.path.join(ROOT, "include", "gorse_b200.h")).read()
+    declared = set(re.findall(r"\b(gorse_b200_[a-z0-9_]+)\s*\(", header)) | set(re.findall(r"\b(GORSE_B200_[A-Z0-9_]+)\b", header))
+    declared |= set(re.findall(r"typedef struct (gorse_b200_[a-z0-9_]+)", header)) | set(re.findall(r"}\s*(gorse_b200_[a-z0-9_]+);", header))
+    used = set()
+    for dp, _, files in os.walk(os.path.join(ROOT, "go")):
+        for f in files:
+            if f.endswith(".go"):
+                txt = open(os.path.join(dp, f)).read()
+                used |= set(re.findall(r"\bC\.((?:gorse_b200|GORSE_B200)_[A-Za-z0-9_]+)", txt))
+                declared |= set(re.findall(r"static\s+[\w\s\*]+?\b(gorse_b200_[a-z0-9_]+)\s*\(", txt))   # helpers of the cgo preamble
+    assert used, "no cgo calls found under go/"
+    missing = sorted(u for u in used if u not in declared)
+    assert not missing, missing
