@@ -106,3 +106,18 @@ def test_go_shim_only_calls_declared_entry_points():
     assert used, "no cgo calls found under go/"
     missing = sorted(u for u in used if u not in declared)
     assert not missing, missing
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (what cgo feeds it to) and as C++11, warnings as errors."""
+    import shutil
+    import subprocess
+
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "gorse_b200.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cc, args in (("gcc", ["-std=c99", "-pedantic"]), ("g++", ["-std=c++11", "-x", "c++"])):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not found")
+        r = subprocess.run([cc, *args, "-Wall", "-Wextra", "-Werror", "-I", inc, "-fsyntax-only", str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
