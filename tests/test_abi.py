@@ -72,6 +72,16 @@ def test_argument_errors_do_not_need_a_device(gb):
     assert b"NULL" in _lib.lib.gorse_b200_last_error()
     assert _lib.lib.gorse_b200_index_create(None, 8, 1, C.byref(h)) == _lib.ERR_ARG
     assert _lib.lib.gorse_b200_ctx_sync(None) == _lib.ERR_ARG
+    # the similarity host functions and the sparse index validate before they touch anything
+    n = C.c_int32(0)
+    assert _lib.lib.gorse_b200_similar_scores(7, 1.0, 0, 1, None, None, 0, None, None, C.byref(n)) == _lib.ERR_ARG
+    assert b"metric" in _lib.lib.gorse_b200_last_error()
+    assert _lib.lib.gorse_b200_index_query_similar(None, 0, 1, 5, 1.0, None, None, None) == _lib.ERR_ARG
+    assert _lib.lib.gorse_b200_bf16_truncate(None, 4, None) == _lib.ERR_ARG
+    assert _lib.lib.gorse_b200_sparse_index_create(None, C.byref(h)) == _lib.ERR_ARG
+    assert _lib.lib.gorse_b200_sparse_index_add(None, None, None, None, 0, None) == _lib.ERR_ARG
+    assert _lib.lib.gorse_b200_sparse_index_search_range(None, 0, 1, 5, None, None, None) == _lib.ERR_ARG
+    assert _lib.lib.gorse_b200_als_epoch(None, 0.06, 0.001) == _lib.ERR_ARG
 
 
 def test_synth_shapes(gb):
