@@ -63,7 +63,7 @@ def test_oracle_als_epoch_matches_line_by_line_transcription(orc):
 
 
 def test_objective_is_monotone_and_reduced_problem_reproduces_rows(orc):
-    """Validates, on the oracle, the two checks the full-size GPU test (tests/test_fullsize_gpu.py, C3) relies on."""
+    """Validates, on the oracle, the two checks the full-size GPU test (tests/test_xl_als_gpu.py) relies on."""
     import gorse_b200 as gb
     from gorse_b200 import synth
 
