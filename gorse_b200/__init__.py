@@ -295,7 +295,7 @@ class BruteforceIndex:
 
 
 class SparseIndex:
-    """EXPERIMENTAL (not yet run on hardware): brute-force Dot search over sparse vectors, the store side of the
+    """Brute-force Dot search over sparse vectors, the store side of the
     tags / users / auto similarity types (storage/vectors/xvec.go:244-248)."""
 
     def __init__(self, ctx):

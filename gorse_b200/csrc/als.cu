@@ -534,13 +534,7 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
     }
 }
 
-// GORSE_B200_ALS_FMA2=1: the Gram register tiles issue FFMA2 (two fp32 FMAs per instruction; the scalar FFMA issues at
-// half the fp32 peak on Blackwell).  Off by default until measured and parity-checked on the GPU (experiment queue).
-static bool als_fma2()
-{
-    static bool f = [] { const char *e = getenv("GORSE_B200_ALS_FMA2"); return e && atoi(e) == 1; }();
-    return f;
-}
+// (FFMA2 register tiles -- fma.rn.f32x2 -- were measured in round 2: 49.3 vs 35.0 ms per C3 epoch, slower; removed.)
 
 static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const int64_t *off)
 {
@@ -552,18 +546,11 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
     if (d <= 128) {
         int T = d <= 16 ? 1 : d <= 32 ? 2 : d <= 64 ? 4 : 8;
         size_t sm = sizeof(float) * 16 * 16 * T;
-        const bool f2 = als_fma2();
         switch (T) {
             case 1: gram_kernel<1, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
-            case 2: if (f2) gram_kernel<2, true><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
-                    else gram_kernel<2, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
-                    break;
-            case 4: if (f2) gram_kernel<4, true><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
-                    else gram_kernel<4, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
-                    break;
-            default: if (f2) gram_kernel<8, true><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
-                     else gram_kernel<8, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p);
-                     break;
+            case 2: gram_kernel<2, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            case 4: gram_kernel<4, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
+            default: gram_kernel<8, false><<<parts, 256, sm, c->stream>>>(X, rows, d, off, cf->scratch.p); break;
         }
     } else {
         gram_generic_kernel<<<parts, 256, 0, c->stream>>>(X, rows, d, off, cf->scratch.p);
@@ -738,12 +725,11 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             const size_t gsm = sizeof(float) * 16 * 16 * T;
             const int nc = cf->als_n_chunks[side];
             auto *ck = als_chunk_gram_kernel<1, false>;
-            const bool f2 = als_fma2();
-            switch (T) {
+                switch (T) {
                 case 1: break;
-                case 2: ck = f2 ? als_chunk_gram_kernel<2, true> : als_chunk_gram_kernel<2, false>; break;
-                case 4: ck = f2 ? als_chunk_gram_kernel<4, true> : als_chunk_gram_kernel<4, false>; break;
-                default: ck = f2 ? als_chunk_gram_kernel<8, true> : als_chunk_gram_kernel<8, false>; break;
+                case 2: ck = als_chunk_gram_kernel<2, false>; break;
+                case 4: ck = als_chunk_gram_kernel<4, false>; break;
+                default: ck = als_chunk_gram_kernel<8, false>; break;
             }
             ck<<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p);
             GB_LAUNCHED(c);

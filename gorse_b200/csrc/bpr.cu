@@ -235,10 +235,9 @@ __device__ __forceinline__ float *item_ref(const BprView &v, int32_t it, int32_t
 // same addresses (one coalesced request per piece), sum their 8 row deltas with shuffles and issue ONE red per piece:
 // 8x fewer operations on the row's L2 atomic units, which otherwise bound the top item (measured: 16 loads + 16 reds
 // per triple on one striped row sustain only ~2*10^8 updates/s).
-// PF (experiment queue, GORSE_B200_HOT_PREFETCH=1): the user row of the entry two rounds ahead is prefetched into L2 as
-// soon as its index has arrived, so that next round's gather (issued one round before use) is an L2 hit instead of an
-// HBM access -- the user table (256 MB at C2) is the only operand of this kernel that does not live in L2.
-template <int C, bool PF>
+// (Prefetching the user row two rounds ahead into L2 was measured in round 2: 3.770 vs 3.772 ms per C2 epoch, no effect;
+// removed.)
+template <int C>
 __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot, const unsigned *begin, const unsigned *first_quad,
                                                             const int32_t *sorted, float lr, float reg)
 {
@@ -313,13 +312,6 @@ __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot
                 dq[c].z += __shfl_xor_sync(0xffffffffu, dq[c].z, sft); dq[c].w += __shfl_xor_sync(0xffffffffu, dq[c].w, sft);
             }
             if (lane < 4) red_row(Qh + sh * c, dq[c]);
-        }
-        if constexpr (PF) {
-            if (u3 >= 0) {
-                const float *pp = v.P + (int64_t)(u3 - v.u_lo) * v.d + 4 * lane4;
-#pragma unroll
-                for (int c = 0; c < C; c++) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + 16 * c));
-            }
         }
 #pragma unroll
         for (int c = 0; c < C; c++) { r.p[c] = rn.p[c]; r.qj[c] = rn.qj[c]; }
@@ -732,14 +724,15 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
             GB_LAUNCHED(c);
             hot_fill_kernel<<<sg, 256, nh * sizeof(unsigned), c->stream>>>(hq, nh, cursor, cf->hot_sorted.p);
             GB_LAUNCHED(c);
-            const int hg = (int)((quad_budget + (unsigned)nh + 63u) / 64u);  // upper bound of quads in use; the rest exit
-            static const bool pf = [] { const char *e = getenv("GORSE_B200_HOT_PREFETCH"); return e && atoi(e) == 1; }();
-            auto *hk = bpr_hot_apply_kernel<1, false>;
+            // upper bound of quads in use (the rest exit): hot_scan_kernel gives slot t ceil(share) <= share + 1 quads, then rounds up to
+            // a multiple of 8 (< +8), so sum k_t < quad_budget + 8 * nh
+            const int hg = (int)((quad_budget + 8u * (unsigned)nh + 63u) / 64u);
+            auto *hk = bpr_hot_apply_kernel<1>;
             switch (C) {
-                case 1: hk = pf ? bpr_hot_apply_kernel<1, true> : bpr_hot_apply_kernel<1, false>; break;
-                case 2: hk = pf ? bpr_hot_apply_kernel<2, true> : bpr_hot_apply_kernel<2, false>; break;
-                case 4: hk = pf ? bpr_hot_apply_kernel<4, true> : bpr_hot_apply_kernel<4, false>; break;
-                default: hk = pf ? bpr_hot_apply_kernel<8, true> : bpr_hot_apply_kernel<8, false>; break;
+                case 1: break;
+                case 2: hk = bpr_hot_apply_kernel<2>; break;
+                case 4: hk = bpr_hot_apply_kernel<4>; break;
+                default: hk = bpr_hot_apply_kernel<8>; break;
             }
             hk<<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg);
             GB_LAUNCHED(c);
@@ -750,7 +743,7 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
     if (c->world > 1) {
         int64_t n = (int64_t)cf->Q.n;
         int g = c->sm_count * 8;
-        if (n % 4 == 0) q_delta_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (const float4 *)cf->Q0.p, n / 4);
+        if (cf->d % 4 == 0) q_delta_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (const float4 *)cf->Q0.p, n / 4);
         else q_delta_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n);
         GB_LAUNCHED(c);
         // per-row damping inputs (see the comment above q_delta_kernel)
@@ -767,7 +760,7 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
         GB_NCCL_API(nc);
         GB_NCCL(nc, AllReduce(cf->Q.p, cf->Q.p, (size_t)n, ncclFloat32, ncclSum, c->comm, c->stream));
         GB_NCCL(nc, AllReduce(cf->xchg.p, cf->xchg.p, (size_t)2 * cf->n_items, ncclFloat32, ncclSum, c->comm, c->stream));
-        if (n % 4 == 0) q_apply_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (float4 *)cf->Q0.p, n / 4, cf->d / 4, cf->xchg.p, cf->n_items);
+        if (cf->d % 4 == 0) q_apply_kernel<<<g, 256, 0, c->stream>>>((float4 *)cf->Q.p, (float4 *)cf->Q0.p, n / 4, cf->d / 4, cf->xchg.p, cf->n_items);
         else q_apply_scalar_kernel<<<g, 256, 0, c->stream>>>(cf->Q.p, cf->Q0.p, n, cf->d, cf->xchg.p, cf->n_items);
         GB_LAUNCHED(c);
     }

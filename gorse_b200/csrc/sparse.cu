@@ -2,9 +2,8 @@
 // types "tags", "users" and "auto" ask their vector store for (storage/vectors/xvec.go:244-248 flat sparse index, :405
 // query; vectors built by appendSparseVector, logics/vector_writer.go:200-209).  SURVEY 8f-1, the row after the dense index.
 //
-// STATUS: written after round 1's GPU budget was spent -- compiled, NOT yet run on hardware; its GPU tests are gated by
-// GORSE_B200_EXPERIMENTAL=1 (tests/test_sparse_gpu.py).  The arithmetic it must reproduce: merge-join dot of two sparse
-// vectors summed in ascending index order, fp32, multiply and add unfused (the test suite's CPU restatement).
+// First hardware run in round 2 (tests/test_sparse_gpu.py green).  The arithmetic it must reproduce: merge-join dot of two
+// sparse vectors summed in ascending index order, fp32, multiply and add unfused (the test suite's CPU restatement).
 //
 // Layout: the vectors as CSR (row -> ascending feature indices + values) and the same entries as CSC (feature -> ascending
 // rows + values, the posting lists).  One warp answers one query row r:

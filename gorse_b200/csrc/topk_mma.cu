@@ -123,17 +123,9 @@ struct Params {
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-// three-input max (Blackwell FMNMX3)
-__device__ __forceinline__ float max3(float a, float b, float c)
-{
-    float r;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
-    return r;
-}
-
-// EPI8: the epilogue tests 8 columns per branch with a 3-input max tree (4 instead of 6 max + 1 instead of 2 compares
-// per 8 columns); experiment queue, selected by GORSE_B200_TOPK_EPI8=1 until measured.
-template <int STAGES, bool EPI8>
+// (An epilogue testing 8 columns per branch with a 3-input max tree was measured in round 2: stage-1 fraction 0.515 vs
+// 0.565 with 4 columns per branch; removed.)
+template <int STAGES>
 __global__ void __launch_bounds__(THREADS, 1)
 topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params P)
 {
@@ -263,25 +255,6 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             }
                         }
                     } else {
-                        if constexpr (EPI8) {
-#pragma unroll
-                            for (int e = 0; e < 32; e += 8) {
-                                const float m1 = max3(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]));
-                                const float m2 = max3(m1, __uint_as_float(v[e + 3]), __uint_as_float(v[e + 4]));
-                                const float m3 = max3(m2, __uint_as_float(v[e + 5]), __uint_as_float(v[e + 6]));
-                                const float mx = fmaxf(m3, __uint_as_float(v[e + 7]));
-                                if (mx >= theta) {
-#pragma unroll
-                                    for (int f = 0; f < 8; f++) {
-                                        const float x = __uint_as_float(v[e + f]);
-                                        if (x >= theta && col0 + e + f < P.n && row_ok) {
-                                            if (cnt < HALF_CAP) { ccol[cnt] = (int32_t)(col0 + e + f); cval[cnt] = x; }
-                                            cnt++;
-                                        }
-                                    }
-                                }
-                            }
-                        } else {
                         // one compare per 4 columns in the common case
 #pragma unroll
                         for (int e = 0; e < 32; e += 4) {
@@ -298,7 +271,6 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 }
                             }
                         }
-                        }  // !EPI8
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -587,9 +559,7 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         return done(st);
     else { ix->w_cq = cq; ix->w_kp = kp; }
     const int64_t fl_off = ix->w_cq;  // the fallback counter sits after the list
-    static const bool epi8 = [] { const char *e = getenv("GORSE_B200_TOPK_EPI8"); return e && atoi(e) == 1; }();
-    auto kern = epi8 ? (stages >= 4 ? mma::topk_mma_kernel<4, true> : stages == 3 ? mma::topk_mma_kernel<3, true> : mma::topk_mma_kernel<2, true>)
-                     : (stages >= 4 ? mma::topk_mma_kernel<4, false> : stages == 3 ? mma::topk_mma_kernel<3, false> : mma::topk_mma_kernel<2, false>);
+    auto kern = stages >= 4 ? mma::topk_mma_kernel<4> : stages == 3 ? mma::topk_mma_kernel<3> : mma::topk_mma_kernel<2>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("search_mma smem attr: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
     for (int64_t off = 0; off < nq; off += cq) {

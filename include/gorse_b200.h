@@ -252,7 +252,7 @@ int32_t gorse_b200_index_query_similar(gorse_b200_index *ix, int64_t q0, int64_t
                                        int32_t *ids_out, double *scores_out, int32_t *count_out);
 
 /* ------------------------------------------------------------------------------------------
- * EXPERIMENTAL (compiled, not yet run on hardware): brute-force search over sparse
+ * Sparse index: brute-force search over sparse
  * vectors with the Dot metric -- what the "tags" / "users" / "auto" similarity types ask their vector
  * store for (storage/vectors/xvec.go:244-248 flat sparse index, :405 query).
  * ---------------------------------------------------------------------------------------- */

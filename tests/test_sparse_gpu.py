@@ -1,14 +1,9 @@
-"""EXPERIMENTAL sparse Dot index (csrc/sparse.cu) against the oracle's sparse brute force and the reference's
-known neighbour orders (logics/item_to_item_test.go:212-316).  The kernel was written after round 1's GPU budget was
-spent and has not run on hardware yet, so these tests only run with GORSE_B200_EXPERIMENTAL=1; the gate goes away once
-they have passed on a B200."""
-import os
-
+"""Sparse Dot index (csrc/sparse.cu) against the oracle's sparse brute force and the reference's known neighbour
+orders (logics/item_to_item_test.go:212-316).  First hardware run: round 2 (4 passed)."""
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("GORSE_B200_EXPERIMENTAL") != "1", reason="experimental: set GORSE_B200_EXPERIMENTAL=1")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture(scope="module")
