@@ -105,18 +105,11 @@ def get_data(wl, seed):
 
 
 def make_shard(wl, rank, world):
-    """This rank's users (seeded per rank) inside a global CSR whose other rows are empty: BPR touches only the
-    rank's own user shard, so the other shards' rows are never read (see DESIGN.md multi-GPU)."""
-    from gorse_b200 import synth
-
+    """This rank's rows of the global user CSR (the C ABI takes ONLY the rank's own rows in a distributed context):
+    users [rank*upr, (rank+1)*upr) of n_users = upr*world, seeded per rank."""
     upr, n_items, fpr, d, _ = WORKLOADS[wl]
     off_l, items = get_data(wl, 1000 + rank)
-    n_users = upr * world
-    off = np.zeros(n_users + 1, np.int64)
-    lo = rank * upr
-    off[lo:lo + upr + 1] = off_l
-    off[lo + upr + 1:] = off_l[-1]
-    return n_users, n_items, d, off, items
+    return upr * world, n_items, d, off_l, items
 
 
 def cpu_baseline(wl, seconds_budget=3.0, prefer_ref=True):

@@ -184,13 +184,17 @@ class CFModel:
         res = _lib.FitResult()
         test_off = np.ascontiguousarray(test_off, np.int64)
         test_items = np.ascontiguousarray(test_items, np.int32)
-        neg_off = np.ascontiguousarray(neg_off, np.int64)
-        neg_items = np.ascontiguousarray(neg_items, np.int32)
+        if neg_off is not None:   # None: the negatives are sampled on the device (params: candidates)
+            neg_off = np.ascontiguousarray(neg_off, np.int64)
+            neg_items = np.ascontiguousarray(neg_items, np.int32)
         cb = _lib.PROGRESS_FN(lambda user, ep, n, ndcg: int(bool(progress(ep, n, ndcg)))) if progress else None
         fn = lib.gorse_b200_als_fit if kind == "als" else lib.gorse_b200_bpr_fit
         check(fn(self.h, C.byref(fp), ptr(test_off), ptr(test_items), ptr(neg_off), ptr(neg_items),
                  C.cast(cb, C.c_void_p) if cb else None, None, C.byref(res)))
         return res
+
+    def eval_plan(self, test_off, test_items, neg_off=None, neg_items=None, n_candidates=100, seed=0, topk=10):
+        return EvalPlan(self, test_off, test_items, neg_off, neg_items, n_candidates, seed, topk)
 
     def evaluate(self, test_off, test_items, neg_off, neg_items, topk=10):
         test_off = np.ascontiguousarray(test_off, np.int64)
@@ -201,6 +205,47 @@ class CFModel:
         check(lib.gorse_b200_cf_evaluate(self.h, ptr(test_off), ptr(test_items), ptr(neg_off), ptr(neg_items), topk,
                                          ptr(out)))
         return out
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class EvalPlan:
+    """cf.Evaluate's inputs resident on the device (gorse_b200_eval_*): test rows + negatives, sampled there when
+    neg_off is None (dataset.SampleUserNegatives, dataset/dataset.go:242-253)."""
+
+    def __init__(self, model, test_off, test_items, neg_off, neg_items, n_candidates, seed, topk):
+        self.model = model
+        test_off = np.ascontiguousarray(test_off, np.int64)
+        test_items = np.ascontiguousarray(test_items, np.int32)
+        if neg_off is not None:
+            neg_off = np.ascontiguousarray(neg_off, np.int64)
+            neg_items = np.ascontiguousarray(neg_items, np.int32)
+        self.rows = len(test_off) - 1
+        h = C.c_void_p()
+        check(lib.gorse_b200_eval_create(model.h, ptr(test_off), ptr(test_items), ptr(neg_off), ptr(neg_items), n_candidates, seed,
+                                         topk, C.byref(h)))
+        self.h = h
+
+    def run(self):
+        out = np.zeros(3, np.float32)
+        check(lib.gorse_b200_eval_run(self.h, ptr(out)))
+        return out
+
+    def negatives(self):
+        off = np.zeros(self.rows + 1, np.int64)
+        check(lib.gorse_b200_eval_negatives(self.h, ptr(off), None))
+        items = np.zeros(int(off[-1]), np.int32)
+        check(lib.gorse_b200_eval_negatives(self.h, ptr(off), ptr(items)))
+        return off, items
+
+    def close(self):
+        if self.h:
+            lib.gorse_b200_eval_destroy(self.h)
+            self.h = None
 
     def __enter__(self):
         return self

@@ -57,6 +57,10 @@ PROTOTYPES = {
     "gorse_b200_bpr_epoch": (C.c_int32, [VP, C.c_float, C.c_float, C.c_int64, C.c_uint64, C.c_int32]),
     "gorse_b200_als_epoch": (C.c_int32, [VP, C.c_float, C.c_float]),
     "gorse_b200_cf_evaluate": (C.c_int32, [VP, VP, VP, VP, VP, C.c_int32, VP]),
+    "gorse_b200_eval_create": (C.c_int32, [VP, VP, VP, VP, VP, C.c_int32, C.c_uint64, C.c_int32, PVP]),
+    "gorse_b200_eval_run": (C.c_int32, [VP, VP]),
+    "gorse_b200_eval_negatives": (C.c_int32, [VP, VP, VP]),
+    "gorse_b200_eval_destroy": (C.c_int32, [VP]),
     "gorse_b200_fit_params_default": (C.c_int32, [C.c_int32, VP]),
     "gorse_b200_bpr_fit": (C.c_int32, [VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "gorse_b200_als_fit": (C.c_int32, [VP, VP, VP, VP, VP, VP, VP, VP, VP]),

@@ -536,11 +536,13 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
 
 // (FFMA2 register tiles -- fma.rn.f32x2 -- were measured in round 2: 49.3 vs 35.0 ms per C3 epoch, slower; removed.)
 
+// S = sum over rows with >= 1 feedback of x x^T.  `X`, `off` and `rows` describe THIS RANK's row range (off is the rank's
+// rebased offsets); in a distributed context the d x d partial sums are all-reduced, so every rank ends with the same bits.
 static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const int64_t *off)
 {
     gorse_b200_ctx *c = cf->ctx;
     const int d = cf->d, dd = d * d;
-    int parts = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, (int64_t)c->sm_count * 2));
+    int parts = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)rows + 63) / 64, (int64_t)c->sm_count * 2));
     size_t need = (size_t)parts * dd;
     if (cf->scratch.n < need) GB_TRY(cf->scratch.alloc(need));
     if (d <= 128) {
@@ -558,6 +560,10 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
     GB_LAUNCHED(c);
     gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, c->stream>>>(cf->scratch.p, parts, dd, cf->gram.p);
     GB_LAUNCHED(c);
+    if (c->world > 1) {
+        GB_NCCL_API(nc);
+        GB_NCCL(nc, AllReduce(cf->gram.p, cf->gram.p, (size_t)dd, ncclFloat32, ncclSum, c->comm, c->stream));
+    }
     return GORSE_B200_OK;
 }
 
@@ -585,10 +591,8 @@ static bool als_grouped(const gorse_b200_cf *cf) { return cf->d % 32 == 0 && cf-
 // rows of `side` (0 users, 1 items) this rank updates: users as in cf_create (cf->u_lo/u_hi), items by the same rule
 static void shard_range(const gorse_b200_cf *cf, int side, int32_t &lo, int32_t &hi)
 {
-    const gorse_b200_ctx *c = cf->ctx;
-    const int32_t rows = side == 0 ? cf->n_users : cf->n_items;
-    lo = (int32_t)((int64_t)rows * c->rank / c->world);
-    hi = (int32_t)((int64_t)rows * (c->rank + 1) / c->world);
+    lo = side == 0 ? cf->u_lo : cf->i_lo;
+    hi = side == 0 ? cf->u_hi : cf->i_hi;
 }
 
 static int32_t prepare_als(gorse_b200_cf *cf)
@@ -597,12 +601,13 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     const int dp = cf->d + 1;
     const bool grouped = als_grouped(cf);
     for (int side = 0; side < 2; side++) {
-        const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
-        int32_t rows = side == 0 ? cf->n_users : cf->n_items;
+        // host offsets hold this rank's rows only, rebased: row r sits at index r - r_lo
+        const int64_t *off = (side == 0 ? cf->h_user_off : cf->h_item_off).data();
         std::vector<int32_t> cls[5];
         // multi-rank: this rank updates its own range of users and of items only
-        int32_t r_lo = 0, r_hi = rows;
+        int32_t r_lo = 0, r_hi = 0;
         shard_range(cf, side, r_lo, r_hi);
+        off -= r_lo;
         for (int32_t r = r_lo; r < r_hi; r++) {
             int64_t n = off[(size_t)r + 1] - off[r];
             int k;
@@ -626,7 +631,7 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     }
     // long rows take the Gram form when d <= 128: cut them into chunks
     for (int side = 0; side < 2 && cf->d <= 128; side++) {
-        const std::vector<int64_t> &off = side == 0 ? cf->h_user_off : cf->h_item_off;
+        const int64_t *off = (side == 0 ? cf->h_user_off : cf->h_item_off).data() - (side == 0 ? cf->u_lo : cf->i_lo);
         std::vector<int32_t> rows((size_t)cf->als_rows_n[side][GB_ALS_LONG]);
         if (rows.empty()) continue;
         GB_CUDA(cudaMemcpy(rows.data(), cf->als_rows[side][GB_ALS_LONG].p, sizeof(int32_t) * rows.size(), cudaMemcpyDeviceToHost));
@@ -792,7 +797,7 @@ extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alph
     const bool multi = c->world > 1;
     GB_TRY(prepare_als(cf));
     DevBuf<float> pred;
-    GB_TRY(pred.alloc((size_t)std::max<int64_t>(1, cf->n_feedback)));
+    GB_TRY(pred.alloc((size_t)std::max<int64_t>(1, std::max(cf->n_feedback, cf->n_item_feedback))));
     int32_t st;
     auto done = [&](int32_t s) {
         cudaStreamSynchronize(c->stream);
@@ -802,7 +807,8 @@ extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alph
     // Multi-rank: Q is replicated and P is range-sharded as for BPR.  The user half-sweep needs only Q, the item
     // half-sweep needs ALL of P, so the epoch works on a full copy P_all: own rows in, user sweep on the own range, ranges
     // exchanged, S^p and the item sweep (own item range) on P_all, item ranges of Q exchanged, own rows of P_all back.
-    // Both Grams are computed in full on every rank from replicated data, so every rank holds bit-identical S^q, S^p, Q.
+    // Each Gram is the all-reduced sum of the ranks' partial Grams over their own row ranges, so every rank holds
+    // bit-identical S^q, S^p and Q (the sums differ from the single-GPU epoch by reassociation only).
     float *P = cf->P.p;
     const int64_t own = (int64_t)(cf->u_hi - cf->u_lo) * cf->d;
     if (multi) {
@@ -813,11 +819,13 @@ extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alph
             if (e != cudaSuccess) { set_error("als_epoch: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
         }
     }
-    if ((st = run_gram(cf, cf->Q.p, cf->n_items, cf->item_off.p))) return done(st);
-    if ((st = run_rows(cf, 0, P, cf->Q.p, cf->user_off.p, cf->user_items.p, reg, alpha, pred.p))) return done(st);
+    // the row kernels index the offsets with GLOBAL row ids: hand them the rank's arrays shifted by the range start
+    const int64_t *uoff = cf->user_off.p - cf->u_lo, *ioff = cf->item_off.p - cf->i_lo;
+    if ((st = run_gram(cf, cf->Q.p + (int64_t)cf->i_lo * cf->d, cf->i_hi - cf->i_lo, cf->item_off.p))) return done(st);
+    if ((st = run_rows(cf, 0, P, cf->Q.p, uoff, cf->user_items.p, reg, alpha, pred.p))) return done(st);
     if (multi && (st = exchange_shards(cf, 0, P))) return done(st);
-    if ((st = run_gram(cf, P, cf->n_users, cf->user_off.p))) return done(st);
-    if ((st = run_rows(cf, 1, cf->Q.p, P, cf->item_off.p, cf->item_users.p, reg, alpha, pred.p))) return done(st);
+    if ((st = run_gram(cf, P + (int64_t)cf->u_lo * cf->d, cf->u_hi - cf->u_lo, cf->user_off.p))) return done(st);
+    if ((st = run_rows(cf, 1, cf->Q.p, P, ioff, cf->item_users.p, reg, alpha, pred.p))) return done(st);
     if (multi) {
         if ((st = exchange_shards(cf, 1, cf->Q.p))) return done(st);
         cudaError_t e = cudaSuccess;

@@ -205,7 +205,7 @@ __device__ __forceinline__ void sample_triple(const BprView &v, uint64_t base, i
     s.x = mix64(base + (uint64_t)step);
     uint32_t ua = s.bounded((uint32_t)v.n_active);
     u = v.active ? __ldg(v.active + ua) : v.u_lo + (int32_t)ua;
-    const UserMeta m = ld_meta(v.meta + u);
+    const UserMeta m = ld_meta(v.meta + (u - v.u_lo));
     const int64_t o = m.off();
     const int64_t len = m.len();
     i = __ldg(v.user_items + o + s.bounded((uint32_t)len));
@@ -683,8 +683,9 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
     gorse_b200_ctx *c = cf->ctx;
     // rank r runs steps [n*r/W, n*(r+1)/W) of the global step stream on its own user shard
     int64_t s0 = n_steps * c->rank / c->world, s1 = n_steps * (c->rank + 1) / c->world;
-    if (s1 > s0) {
-        if (cf->n_active == 0) { set_error("no user with feedback in this shard"); return GORSE_B200_ERR_STATE; }
+    if (s1 > s0 && cf->n_active == 0 && c->world == 1) { set_error("no user with feedback"); return GORSE_B200_ERR_STATE; }
+    // a rank whose shard has no feedback runs zero local steps and still joins the exchange below
+    if (s1 > s0 && cf->n_active > 0) {
         BprView v = make_view(cf);
         const int C = cf->d / 16;
         const bool use_hot = cf->n_hot > 0 && cf->d % 16 == 0 && (C == 1 || C == 2 || C == 4 || C == 8) && scatter == GORSE_B200_SCATTER_ATOMIC;
@@ -750,12 +751,12 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
         float *psq = cf->xchg.p + 2 * (int64_t)cf->n_items;
         GB_CUDA(cudaMemsetAsync(psq, 0, 4 * sizeof(float), c->stream));
         const int64_t n_rows = cf->u_hi - cf->u_lo;
-        if (n_rows > 0 && s1 > s0) {
+        if (n_rows > 0 && s1 > s0 && cf->n_active > 0) {
             const int64_t n_sample = std::min<int64_t>(n_rows, 65536), stride = std::max<int64_t>(1, n_rows / n_sample);
             p_norm_sample_kernel<<<(int)std::min<int64_t>(div_up(n_sample * 32, 256), c->sm_count * 8), 256, 0, c->stream>>>(cf->P.p, n_rows, cf->d, stride, n_sample, psq);
             GB_LAUNCHED(c);
         }
-        xchg_prepare_kernel<<<(int)std::min<int64_t>(div_up(cf->n_items, 256), c->sm_count * 8), 256, 0, c->stream>>>(cf->item_rate.p, cf->n_items, (float)(s1 - s0), lr, reg, cf->d, cf->xchg.p);
+        xchg_prepare_kernel<<<(int)std::min<int64_t>(div_up(cf->n_items, 256), c->sm_count * 8), 256, 0, c->stream>>>(cf->item_rate.p, cf->n_items, (float)(cf->n_active > 0 ? s1 - s0 : 0), lr, reg, cf->d, cf->xchg.p);
         GB_LAUNCHED(c);
         GB_NCCL_API(nc);
         GB_NCCL(nc, AllReduce(cf->Q.p, cf->Q.p, (size_t)n, ncclFloat32, ncclSum, c->comm, c->stream));

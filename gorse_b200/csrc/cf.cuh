@@ -3,9 +3,10 @@
 // HBM layout (all row-major, natural element order so every kernel and the host mirror agree):
 //   P        [n_local_users x d] fp32   user factors of this rank's user shard (all users when world = 1)
 //   Q        [n_items x d]       fp32   item factors (replicated across ranks)
-//   user_off [n_users + 1] int64, user_items [|R|] int32   R_u, each row sorted ascending
-//   item_off [n_items + 1] int64, item_users [|R|] int32   R_i (ALS only)
-//   active   [n_active] int32    users of this shard with >= 1 feedback, ascending
+//   user_off [n_local_users + 1] int64, user_items [|R_local|] int32   R_u of the shard's users (row u at index u - u_lo,
+//            offsets rebased to 0), each row sorted ascending;  user_meta likewise indexed by u - u_lo
+//   item_off [n_local_items + 1] int64, item_users [...] int32         R_i of the shard's items (ALS only)
+//   active   [n_active] int32    users of this shard with >= 1 feedback, ascending (global ids)
 //
 // Row -> lane mapping used by every d % 16 == 0 kernel ("quad" layout): 4 lanes own one row.  For the
 // c-th 16-float chunk, lane l (0..3) holds the float4 at floats [16c + 4l, 16c + 4l + 4).  A quad
@@ -34,7 +35,10 @@ struct gorse_b200_cf {
     gorse_b200_ctx *ctx = nullptr;
     int32_t n_users = 0, n_items = 0, d = 0;
     int32_t u_lo = 0, u_hi = 0;  // user shard [u_lo, u_hi) owned by this rank
-    int64_t n_feedback = 0;
+    int32_t i_lo = 0, i_hi = 0;  // item shard (the rows of the item CSR this rank holds and updates in the eALS item sweep)
+    int64_t n_feedback = 0;         // entries of this rank's user rows
+    int64_t n_feedback_global = 0;  // over all ranks (== n_feedback when world = 1)
+    int64_t n_item_feedback = 0;    // entries of this rank's item rows
     int32_t n_active = 0;
     bool has_item_csr = false;
     gb::DevBuf<float> P, Q, Q0;

@@ -25,17 +25,22 @@ int32_t fit_loop(gorse_b200_cf *cf, bool als, const gorse_b200_fit_params *p, co
     *res = gorse_b200_fit_result{};
     // Init (model.go:414 / :615)
     GB_TRY(gorse_b200_cf_init_normal(cf, p->init_mean, p->init_stddev, p->seed));
-    GB_TRY(gorse_b200_cf_evaluate(cf, ev.test_off, ev.test_items, ev.neg_off, ev.neg_items, p->topk, score));  // :433 / :630
+    // Evaluate's inputs go to the device once per Fit; without caller-sampled negatives they are drawn there
+    // (testSet.SampleUserNegatives(trainSet, Candidates) with NewRandomGenerator(0), evaluator.go:42, dataset.go:244)
+    gorse_b200_eval *plan = nullptr;
+    GB_TRY(gorse_b200_eval_create(cf, ev.test_off, ev.test_items, ev.neg_off, ev.neg_items, p->candidates, 0, p->topk, &plan));
+    struct PlanGuard { gorse_b200_eval *p; ~PlanGuard() { gorse_b200_eval_destroy(p); } } guard{plan};
+    GB_TRY(gorse_b200_eval_run(plan, score));  // :433 / :630
     scores.emplace_back(0, score[0]);
     int32_t epochs_run = 0;
     for (int32_t epoch = 1; epoch <= p->n_epochs; epoch++) {
         if (als) GB_TRY(gorse_b200_als_epoch(cf, p->reg, p->alpha));
-        else GB_TRY(gorse_b200_bpr_epoch(cf, p->lr, p->reg, cf->n_feedback, p->seed + (uint64_t)epoch, GORSE_B200_SCATTER_ATOMIC));
+        else GB_TRY(gorse_b200_bpr_epoch(cf, p->lr, p->reg, cf->n_feedback_global, p->seed + (uint64_t)epoch, GORSE_B200_SCATTER_ATOMIC));
         epochs_run = epoch;
         bool evaluated = false;
         // cross validation cadence, model.go:496 / :741
         if ((p->verbose > 0 && epoch % p->verbose == 0) || epoch == p->n_epochs) {
-            GB_TRY(gorse_b200_cf_evaluate(cf, ev.test_off, ev.test_items, ev.neg_off, ev.neg_items, p->topk, score));
+            GB_TRY(gorse_b200_eval_run(plan, score));
             scores.emplace_back(epoch, score[0]);
             evaluated = true;
         }
@@ -72,6 +77,7 @@ int32_t check_params(const gorse_b200_fit_params *p, const gorse_b200_fit_result
     GB_CHECK_ARG(p != nullptr && res != nullptr, "NULL params/result");
     GB_CHECK_ARG(p->n_epochs >= 0, "negative n_epochs");
     GB_CHECK_ARG(p->topk >= 1, "topk must be >= 1");
+    GB_CHECK_ARG(p->candidates >= 0, "negative candidates");
     return GORSE_B200_OK;
 }
 

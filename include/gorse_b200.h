@@ -83,11 +83,18 @@ int32_t gorse_b200_host_free(void *p);
  * model/cf/model.go:118-127) and the dataset.CFSplit accessors GetUserFeedback/GetItemFeedback
  * (dataset/dataset.go:40-60) flattened to CSR by the shim.
  *
- * user_off[n_users+1], user_items[user_off[n_users]] : R_u  (any order, duplicates allowed; the
- *     device copy is sorted per row for the negative-sampling membership test)
- * item_off[n_items+1], item_users[...]               : R_i  (may be NULL when ALS is not used)
- * In a distributed context every rank passes the FULL CSR; rank r trains users
- * [r*U/world, (r+1)*U/world) and owns those rows of P; Q is replicated.
+ * user_off[rows+1], user_items : R_u  (any order inside a row, duplicates allowed; the device copy is sorted
+ *     per row for the negative-sampling membership test)
+ * item_off[rows+1], item_users : R_i  (may be NULL when ALS is not used)
+ * Offsets need not start at 0: user_items / item_users point at the entry user_off[0] / item_off[0] refers to, so a
+ * slice of a larger CSR can be passed without rebasing.
+ *
+ * One GPU (world = 1): rows = all n_users / n_items.
+ * Distributed context: n_users / n_items stay GLOBAL, but every rank passes ONLY ITS OWN ROWS --
+ * users [n_users*r/W, n_users*(r+1)/W) and items [n_items*r/W, n_items*(r+1)/W) -- so host work, upload and HBM
+ * per rank are 1/W of the job (BASELINE configs[4]: 10 M users x 200 M feedback over 8 GPUs).  Rank r owns those rows
+ * of P; Q is replicated.  Collective: all ranks must call (the global feedback count is all-reduced, and a rank whose
+ * arguments fail validation makes every rank fail instead of hanging the others).
  * ---------------------------------------------------------------------------------------- */
 int32_t gorse_b200_cf_create(gorse_b200_ctx *ctx, int32_t n_users, int32_t n_items, int32_t n_factors,
                              const int64_t *user_off, const int32_t *user_items,
@@ -151,10 +158,28 @@ int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alpha);
  * Recall at topk.  test CSR: test positives per user; neg CSR: sampled negatives per user
  * (dataset.SampleUserNegatives, dataset/dataset.go:242-256 -- sampled by the caller).
  * out[3] = {NDCG, Precision, Recall}.
+ * Distributed context: every rank passes the rows of ITS users (as in gorse_b200_cf_create); the per-user metrics are
+ * summed per rank and all-reduced, so every rank returns the global score (the reference with Jobs = W workers).
+ * Collective.
  * ---------------------------------------------------------------------------------------- */
 int32_t gorse_b200_cf_evaluate(gorse_b200_cf *cf, const int64_t *test_off, const int32_t *test_items,
                                const int64_t *neg_off, const int32_t *neg_items, int32_t topk,
                                float *out);
+/* The same in three steps, so that Fit's repeated evaluations (every Verbose epochs, model/cf/model.go:496-507) upload
+ * their inputs once: gorse_b200_eval_create puts the test rows and the negatives in HBM, gorse_b200_eval_run scores
+ * the model's CURRENT factors.  With neg_off == NULL the negatives are sampled on the device the way
+ * testSet.SampleUserNegatives(trainSet, n_candidates) does (dataset/dataset.go:242-253 -> util.SampleInt32,
+ * common/util/random.go:108-132: n_candidates distinct items outside train(u) and test(u); all remaining items, ascending,
+ * when fewer are left) -- the reference caches them per dataset (:243), the plan per Fit.  The Go math/rand stream is not
+ * reproducible: draws come from the library's counter RNG under `seed`.  gorse_b200_eval_negatives returns
+ * what was sampled: neg_off_out[rows+1]; neg_items_out may be NULL to learn the size (neg_off_out[rows]) first. */
+typedef struct gorse_b200_eval gorse_b200_eval;
+int32_t gorse_b200_eval_create(gorse_b200_cf *cf, const int64_t *test_off, const int32_t *test_items,
+                               const int64_t *neg_off, const int32_t *neg_items, int32_t n_candidates, uint64_t seed,
+                               int32_t topk, gorse_b200_eval **out);
+int32_t gorse_b200_eval_run(gorse_b200_eval *ev, float *out);
+int32_t gorse_b200_eval_negatives(gorse_b200_eval *ev, int64_t *neg_off_out, int32_t *neg_items_out);
+int32_t gorse_b200_eval_destroy(gorse_b200_eval *ev);
 
 /* ------------------------------------------------------------------------------------------
  * Whole Fit.  Replaces cf.BPR.Fit / cf.ALS.Fit (model/cf/model.go:408-530, 609-775): Init, Evaluate at
@@ -163,6 +188,8 @@ int32_t gorse_b200_cf_evaluate(gorse_b200_cf *cf, const int64_t *test_off, const
  * loop in Go and call the per-epoch entry points.  Hyper-parameters are model.Params
  * (model/params.go) + cf.FitConfig (model/cf/model.go:50-65); FitConfig.Jobs has no equivalent.
  * The factor tables of `cf` are created with n_factors = params->n_factors by the caller.
+ * neg_off / neg_items may be NULL: the negatives are then sampled on the device (gorse_b200_eval_create), which is what
+ * the reference's Fit does itself.  In a distributed context the test rows are the rank's own users'.
  * ---------------------------------------------------------------------------------------- */
 typedef struct {
     int32_t n_factors;   /* NFactors, default 16 */
@@ -174,7 +201,7 @@ typedef struct {
     float alpha;         /* Alpha (eALS weight), ALS only, default 0.001 */
     uint64_t seed;       /* RandomState */
     int32_t verbose;     /* FitConfig.Verbose, default 10 */
-    int32_t candidates;  /* FitConfig.Candidates, default 100 (the caller samples the negatives) */
+    int32_t candidates;  /* FitConfig.Candidates, default 100: negatives per user when neg_off == NULL (sampled on the device) */
     int32_t topk;        /* FitConfig.TopK, default 10 */
     int32_t patience;    /* FitConfig.Patience, default 0 = no early stopping */
 } gorse_b200_fit_params;

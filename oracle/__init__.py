@@ -70,6 +70,7 @@ def _sig(L):
     L.gbo_bpr_step.argtypes = [F32, F32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float]
     L.gbo_bpr_apply_triples.argtypes = [F32, F32, C.c_int32, I32, C.c_int64, C.c_float, C.c_float]
     L.gbo_bpr_sample_triples.argtypes = [C.c_int32, I64, I32, I32, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, I32]
+    L.gbo_sample_user_negatives.argtypes = [C.c_int32, C.c_int32, C.c_int32, I64, I32, I64, I32, C.c_int32, C.c_uint64, I64, C.c_void_p]
     L.gbo_bpr_epoch_threads.restype = C.c_double
     L.gbo_bpr_epoch_threads.argtypes = [F32, F32, C.c_int32, C.c_int32, I64, I32, I32, C.c_int32, C.c_uint64,
                                         C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32]
@@ -159,6 +160,17 @@ def bpr_sample_triples(n_items, user_off, user_items, active, seed, first_step, 
     lib().gbo_bpr_sample_triples(n_items, i64(user_off), i32(user_items), i32(active), len(active), seed,
                                  first_step, n, out)
     return out
+
+
+def sample_user_negatives(n_items, train_off, train_items, test_off, test_items, n_cand, seed=0, u_base=0):
+    """dataset.SampleUserNegatives with the library's counter RNG; train rows sorted ascending."""
+    U = len(train_off) - 1
+    off = np.zeros(U + 1, np.int64)
+    a = (n_items, U, u_base, i64(train_off), i32(train_items), i64(test_off), i32(test_items), n_cand, seed)
+    lib().gbo_sample_user_negatives(*a, off, None)
+    items = np.zeros(int(off[-1]), np.int32)
+    lib().gbo_sample_user_negatives(*a, off, items.ctypes.data_as(C.c_void_p))
+    return off, items
 
 
 def bpr_epoch_threads(P, Q, user_off, user_items, active, seed, n_steps, lr, reg, n_threads, use_ref=False):

@@ -519,6 +519,53 @@ void gbo_bpr_sample_triples(int32_t n_items, const int64_t *user_off, const int3
         sample_one(n_items, user_off, user_items, active_users, n_active, base, first_step + t, uij_out + 3 * t);
 }
 
+/* ---- dataset.SampleUserNegatives (dataset/dataset.go:242-253) -> util.SampleInt32 (common/util/random.go:108-132).
+ * Per user: the union of train(u) and test(u) is excluded; when n_cand >= n_items - |excluded| every remaining item is
+ * returned ascending (:116-122), else items are drawn uniformly and rejected while excluded or already drawn (:124-130).
+ * Go's math/rand stream cannot be reproduced: the draws come from the counter RNG shared with the CUDA
+ * path (stream = mix64(seed ^ C) + global user id).  train rows must be sorted ascending (the device copy is).
+ * Two calls: neg_items_out == NULL fills neg_off_out only. */
+void gbo_sample_user_negatives(int32_t n_items, int32_t n_users, int32_t u_base, const int64_t *train_off, const int32_t *train_items,
+                               const int64_t *test_off, const int32_t *test_items, int32_t n_cand, uint64_t seed,
+                               int64_t *neg_off_out, int32_t *neg_items_out)
+{
+    const uint64_t base = mix64(seed ^ 0xbb67ae8584caa73bull);
+    neg_off_out[0] = 0;
+    for (int32_t u = 0; u < n_users; u++) {
+        const int32_t *tr = train_items + train_off[u], *te = test_items + test_off[u];
+        const int64_t ntr = train_off[u + 1] - train_off[u], nte = test_off[u + 1] - test_off[u];
+        int64_t card = 0;
+        for (int64_t a = 0; a < ntr; a++) if (a == 0 || tr[a] != tr[a - 1]) card++;
+        for (int64_t a = 0; a < nte; a++) {
+            int dup = row_contains(tr, ntr, te[a]);
+            for (int64_t b = 0; b < a && !dup; b++) dup = te[b] == te[a];
+            if (!dup) card++;
+        }
+        const int64_t n = (int64_t)n_cand >= (int64_t)n_items - card ? (int64_t)n_items - card : (int64_t)n_cand;
+        neg_off_out[u + 1] = neg_off_out[u] + n;
+        if (!neg_items_out) continue;
+        int32_t *out = neg_items_out + neg_off_out[u];
+        int64_t k = 0;
+        if (n < n_cand) {
+            for (int32_t v = 0; v < n_items && k < n; v++) {
+                int ex = row_contains(tr, ntr, v);
+                for (int64_t a = 0; a < nte && !ex; a++) ex = te[a] == v;
+                if (!ex) out[k++] = v;
+            }
+            continue;
+        }
+        sstream s;
+        s.x = mix64(base + (uint64_t)(u_base + u));
+        while (k < n) {
+            const int32_t v = (int32_t)s_bounded(&s, (uint32_t)n_items);
+            int ex = row_contains(tr, ntr, v);
+            for (int64_t a = 0; a < nte && !ex; a++) ex = te[a] == v;
+            for (int64_t b = 0; b < k && !ex; b++) ex = out[b] == v;
+            if (!ex) out[k++] = v;
+        }
+    }
+}
+
 static double now_sec(void)
 {
     struct timespec ts;

@@ -64,6 +64,10 @@ void gbo_bpr_sample_triples(int32_t n_items, const int64_t *user_off, const int3
                             const int32_t *active_users, int32_t n_active,
                             uint64_t seed, int64_t first_step, int64_t n, int32_t *uij_out);
 /* multi-threaded Hogwild epoch used as the CPU baseline (not a parity target): returns seconds */
+/* dataset.SampleUserNegatives, dataset/dataset.go:242-253 + common/util/random.go:108-132 (our counter RNG) */
+void gbo_sample_user_negatives(int32_t n_items, int32_t n_users, int32_t u_base, const int64_t *train_off, const int32_t *train_items,
+                               const int64_t *test_off, const int32_t *test_items, int32_t n_cand, uint64_t seed,
+                               int64_t *neg_off_out, int32_t *neg_items_out);
 double gbo_bpr_epoch_threads(float *P, float *Q, int32_t n_items, int32_t d,
                              const int64_t *user_off, const int32_t *user_items,
                              const int32_t *active_users, int32_t n_active,

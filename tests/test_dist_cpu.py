@@ -20,12 +20,10 @@ if rank == 0:
     idbuf = torch.frombuffer(bytearray(range(128)), dtype=torch.uint8).clone()
 dist.broadcast(idbuf, 0)
 assert bytes(idbuf.numpy().tobytes()) == bytes(range(128))
-# weak-scaling shard: this rank's users are populated, the others' rows are empty
+# weak-scaling shard: a rank holds (and hands to the C ABI) only its own users' rows
 bench.WORKLOADS["tiny"] = (300, 50, 2000, 16, "tiny")
 n_users, n_items, d, off, items = bench.make_shard("tiny", rank, world)
-assert n_users == 300 * world and 300 <= off[-1] == items.size <= 2000
-lo = rank * 300
-assert off[lo] == 0 and off[lo + 300] == items.size and np.all(np.diff(off[:lo + 1]) == 0) and np.all(np.diff(off[lo + 300:]) == 0)
+assert n_users == 300 * world and len(off) == 301 and off[0] == 0 and 300 <= off[-1] == items.size <= 2000
 # max over ranks
 t = torch.tensor([float(rank + 1)], dtype=torch.float64)
 dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -49,3 +49,34 @@ def test_reference_known_answer(gb, orc):
         m.set_factors(P, Q)
         out = m.evaluate(test_off, test_items, np.array(neg_off, np.int64), np.array(neg_items, np.int32), 4)
     assert out[1] == np.float32(0.625)
+
+
+@pytest.mark.parametrize("I,n_cand", [(250, 100), (40, 100), (120, 30)])
+def test_device_negatives_equal_the_oracle_sampler(gb, orc, I, n_cand):
+    """gorse_b200_eval_create(neg_off = NULL) samples dataset.SampleUserNegatives on the device: identical int32 lists to the
+    oracle's restatement on the shared counter RNG, incl. the "fewer than n_cand items left -> all of them, ascending"
+    branch (common/util/random.go:116-122), users without test items, duplicate test items."""
+    from gorse_b200 import synth
+
+    U, d = 500, 16
+    off, items = synth.make_feedback(U, I, 6000, seed=I, n_clusters=4)
+    train, test = synth.leave_one_out(off, items, seed=1)
+    to, ti = test[0].copy(), test[1].copy()
+    rng = np.random.default_rng(1)
+    P = rng.standard_normal((U, d)).astype(np.float32)
+    Q = rng.standard_normal((I, d)).astype(np.float32)
+    with gb.Context(0) as ctx, gb.CFModel(ctx, U, I, d, train[0], train[1]) as m:
+        m.set_factors(P, Q)
+        with m.eval_plan(to, ti, None, None, n_candidates=n_cand, seed=5, topk=10) as plan:
+            noff, nitems = plan.negatives()
+            got = plan.run()
+            m.set_factors(Q[:1].repeat(U, 0) * 0 + P[::-1], Q)     # the plan scores the CURRENT factors
+            got2 = plan.run()
+    ooff, oitems = orc.sample_user_negatives(I, train[0], train[1], to, ti, n_cand, seed=5)
+    assert noff.tolist() == ooff.tolist() and nitems.tolist() == oitems.tolist()
+    for u in range(0, U, 17):   # distinct, outside train and test
+        row = nitems[noff[u]:noff[u + 1]]
+        excl = set(train[1][train[0][u]:train[0][u + 1]].tolist()) | set(ti[to[u]:to[u + 1]].tolist())
+        assert len(set(row.tolist())) == len(row) == min(n_cand, I - len(excl)) and not (set(row.tolist()) & excl)
+    assert got.tobytes() == orc.evaluate(P, Q, to, ti, noff, nitems, 10).tobytes()
+    assert got2.tobytes() == orc.evaluate(np.ascontiguousarray(P[::-1]), Q, to, ti, noff, nitems, 10).tobytes()

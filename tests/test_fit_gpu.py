@@ -47,3 +47,14 @@ def test_early_stopping_and_cancel(gb, data):
         # cancellation (ctx.Err() != nil): zero Score like the reference (model.go:491-493)
         res = m.fit("bpr", test[0], test[1], neg[0], neg[1], progress=lambda ep, n, s: ep >= 3, n_epochs=50, verbose=10)
         assert res.cancelled and res.epochs_run == 3 and (res.ndcg, res.precision, res.recall) == (0.0, 0.0, 0.0)
+
+
+def test_fit_samples_its_own_negatives(gb, orc, data):
+    """neg_off = NULL: Fit draws the negatives itself like the reference's Evaluate (evaluator.go:42, seed 0)."""
+    U, I, train, test, neg, ioff, iusers = data
+    with gb.Context(0) as ctx, gb.CFModel(ctx, U, I, 16, train[0], train[1]) as m:
+        res = m.fit("bpr", test[0], test[1], None, None, n_epochs=10, verbose=5, seed=3, candidates=50)
+        P, Q = m.get_factors()
+    noff, nitems = orc.sample_user_negatives(I, train[0], train[1], test[0], test[1], 50, seed=0)
+    want = orc.evaluate(P, Q, test[0], test[1], noff, nitems, 10)
+    assert (res.ndcg, res.precision, res.recall) == tuple(want) and res.ndcg > 0.15
