@@ -53,6 +53,7 @@ func NewB200Bruteforce(dim int, metric B200Metric) (*B200Bruteforce, error) {
 
 // Add appends one vector and returns the length after the append, like Bruteforce.Add (bruteforce.go:33-37).
 func (b *B200Bruteforce) Add(v []float32) int {
+	defer runtime.KeepAlive(b) // the finalizer must not destroy the handles while a C call is using them
 	var n C.int64_t
 	if st := C.gorse_b200_index_add(b.ix, (*C.float)(unsafe.Pointer(&v[0])), 1, &n); st != 0 {
 		panic(C.GoString(C.gorse_b200_last_error())) // the reference's Add cannot fail
@@ -62,6 +63,7 @@ func (b *B200Bruteforce) Add(v []float32) int {
 
 // AddBatch uploads n vectors stored contiguously (one PCIe copy instead of n).
 func (b *B200Bruteforce) AddBatch(flat []float32) int {
+	defer runtime.KeepAlive(b) // the finalizer must not destroy the handles while a C call is using them
 	var n C.int64_t
 	if st := C.gorse_b200_index_add(b.ix, (*C.float)(unsafe.Pointer(&flat[0])), C.int64_t(len(flat)/b.dim), &n); st != 0 {
 		panic(C.GoString(C.gorse_b200_last_error()))
@@ -79,6 +81,7 @@ func collect(idx []int32, dist []float32, n int32) []lo.Tuple2[int, float32] {
 
 // SearchIndex never returns q itself; out-of-range q is an error (bruteforce.go:39-63).
 func (b *B200Bruteforce) SearchIndex(q, k int, prune0 bool) ([]lo.Tuple2[int, float32], error) {
+	defer runtime.KeepAlive(b) // the finalizer must not destroy the handles while a C call is using them
 	idx, dist := make([]int32, max(k, 1)), make([]float32, max(k, 1))
 	var cnt C.int32_t
 	qi := C.int64_t(q)
@@ -94,6 +97,7 @@ func (b *B200Bruteforce) SearchIndex(q, k int, prune0 bool) ([]lo.Tuple2[int, fl
 
 // SearchVector mirrors bruteforce.go:65-83 (a NaN distance panics like heap.PriorityQueue.Push, pq.go:82-83).
 func (b *B200Bruteforce) SearchVector(q []float32, k int, prune0 bool) []lo.Tuple2[int, float32] {
+	defer runtime.KeepAlive(b) // the finalizer must not destroy the handles while a C call is using them
 	idx, dist := make([]int32, max(k, 1)), make([]float32, max(k, 1))
 	var cnt C.int32_t
 	st := C.gorse_b200_index_search_vectors(b.ix, (*C.float)(unsafe.Pointer(&q[0])), 1, C.int32_t(k),
@@ -107,6 +111,7 @@ func (b *B200Bruteforce) SearchVector(q []float32, k int, prune0 bool) []lo.Tupl
 // AllNeighbors returns the k nearest neighbours of every stored vector in [q0, q1): what item-to-item / user-to-user
 // ask their vector store for (logics/item_to_item.go:50-62), in one call.
 func (b *B200Bruteforce) AllNeighbors(q0, q1, k int, prune0 bool) ([][]lo.Tuple2[int, float32], error) {
+	defer runtime.KeepAlive(b) // the finalizer must not destroy the handles while a C call is using them
 	nq := q1 - q0
 	idx, dist, cnt := make([]int32, max(nq*k, 1)), make([]float32, max(nq*k, 1)), make([]int32, max(nq, 1))
 	st := C.gorse_b200_index_search_range(b.ix, C.int64_t(q0), C.int64_t(q1), C.int32_t(k), C.int32_t(lo.Ternary(prune0, 1, 0)),
@@ -131,6 +136,7 @@ type SimilarScore struct {
 // logics/user_to_user.go:50-86) for every stored vector in [q0, q1) in one call: the n nearest neighbours without the
 // vector itself, Dot scores <= 0 dropped, Euclidean mapped to 1/(1+dist); scoreScale is .5 for type "auto".
 func (b *B200Bruteforce) QuerySimilar(q0, q1, n int, scoreScale float64) ([][]SimilarScore, error) {
+	defer runtime.KeepAlive(b) // the finalizer must not destroy the handles while a C call is using them
 	nq := q1 - q0
 	ids, scores, cnt := make([]int32, max(nq*n, 1)), make([]float64, max(nq*n, 1)), make([]int32, max(nq, 1))
 	st := C.gorse_b200_index_query_similar(b.ix, C.int64_t(q0), C.int64_t(q1), C.int32_t(n), C.double(scoreScale),

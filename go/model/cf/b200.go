@@ -28,7 +28,6 @@ import "C"
 import (
 	"context"
 	"errors"
-	"runtime"
 	"runtime/cgo"
 	"sync"
 	"unsafe"
@@ -87,35 +86,26 @@ func i32ptr(s []int32) *C.int32_t {
 	return (*C.int32_t)(unsafe.Pointer(&s[0]))
 }
 
-// pinnedMatrix is the flat page-locked host mirror behind UserFactor / ItemFactor ([][]float32 row views into it),
-// so master's row-by-row reads (master/tasks.go:946,969) need no per-row allocation (SURVEY 8b "ownership").
-type pinnedMatrix struct {
-	ptr  unsafe.Pointer
-	flat []float32
-	rows [][]float32
+// flatMatrix is the host mirror behind UserFactor / ItemFactor: ONE flat Go-owned []float32 per table with [][]float32
+// row views into it, so master's row-by-row reads (master/tasks.go:946,969) need no per-row allocation (SURVEY 8b
+// "ownership").  The backing array is ordinary Go memory: the row slices stored in BaseMatrixFactorization keep it alive
+// for exactly as long as the model is reachable, Clear() (model/cf/model.go:294-307) drops it with the rest of the model,
+// and no finalizer or C allocation is involved (round 1 kept the rows in cudaHostAlloc memory behind a finalizer that
+// could fire while the rows were still in use).  gorse_b200_cf_get_factors copies into it during the call only.
+func newFlatMatrix(n, d int) (flat []float32, rows [][]float32) {
+	flat = make([]float32, n*d)
+	rows = make([][]float32, n)
+	for i := range rows {
+		rows[i] = flat[i*d : (i+1)*d : (i+1)*d]
+	}
+	return flat, rows
 }
 
-func newPinnedMatrix(n, d int) (*pinnedMatrix, error) {
-	m := &pinnedMatrix{}
-	if err := b200Error(C.gorse_b200_host_alloc(C.size_t(n*d*4), &m.ptr)); err != nil {
-		return nil, err
-	}
-	if n*d > 0 {
-		m.flat = unsafe.Slice((*float32)(m.ptr), n*d)
-	}
-	m.rows = make([][]float32, n)
-	for i := range m.rows {
-		m.rows[i] = m.flat[i*d : (i+1)*d : (i+1)*d]
-	}
-	runtime.SetFinalizer(m, func(m *pinnedMatrix) { C.gorse_b200_host_free(m.ptr) })
-	return m, nil
-}
-
-func (m *pinnedMatrix) cptr() *C.float {
-	if len(m.flat) == 0 {
+func f32ptr(s []float32) *C.float {
+	if len(s) == 0 {
 		return nil
 	}
-	return (*C.float)(m.ptr)
+	return (*C.float)(unsafe.Pointer(&s[0]))
 }
 
 type fitProgress struct {
@@ -125,7 +115,7 @@ type fitProgress struct {
 
 //export gorseB200Progress
 func gorseB200Progress(user unsafe.Pointer, epoch, nEpochs C.int32_t, ndcg C.float) C.int32_t {
-	p := cgo.Handle(user).Value().(*fitProgress)
+	p := (*(*cgo.Handle)(user)).Value().(*fitProgress) // user = &handle, the documented way to carry a Handle in a void*
 	p.span.Add(1) // model/cf/model.go:519
 	if p.ctx.Err() != nil {
 		return 1 // cancelled -> Fit returns Score{} (:491-493)
@@ -146,7 +136,8 @@ func fitB200(ctx context.Context, base *BaseMatrixFactorization, als bool, param
 	uOff, uIdx := flattenCSR(trainSet.GetUserFeedback())
 	iOff, iIdx := flattenCSR(trainSet.GetItemFeedback())
 	tOff, tIdx := flattenCSR(valSet.GetUserFeedback())
-	nOff, nIdx := flattenCSR(valSet.SampleUserNegatives(trainSet, config.Candidates)) // dataset/dataset.go:242-256
+	// negatives: NULL -> sampled on the device by the library (dataset.SampleUserNegatives semantics, params.candidates per
+	// user; the Go math/rand stream is not reproducible either way, SURVEY F9)
 
 	var cf *C.gorse_b200_cf
 	// the library copies during the call and keeps no Go pointer (cgo rule)
@@ -165,14 +156,13 @@ func fitB200(ctx context.Context, base *BaseMatrixFactorization, als bool, param
 	params.verbose, params.candidates = C.int32_t(config.Verbose), C.int32_t(config.Candidates)
 	params.topk, params.patience = C.int32_t(config.TopK), C.int32_t(config.Patience)
 	var res C.gorse_b200_fit_result
-	fit := C.gorse_b200_bpr_fit
 	var st C.int32_t
 	if als {
-		st = C.gorse_b200_als_fit(cf, &params, i64ptr(tOff), i32ptr(tIdx), i64ptr(nOff), i32ptr(nIdx),
-			C.gorse_b200_progress_ptr(), unsafe.Pointer(h), &res)
+		st = C.gorse_b200_als_fit(cf, &params, i64ptr(tOff), i32ptr(tIdx), nil, nil,
+			C.gorse_b200_progress_ptr(), unsafe.Pointer(&h), &res)
 	} else {
-		st = fit(cf, &params, i64ptr(tOff), i32ptr(tIdx), i64ptr(nOff), i32ptr(nIdx),
-			C.gorse_b200_progress_ptr(), unsafe.Pointer(h), &res)
+		st = C.gorse_b200_bpr_fit(cf, &params, i64ptr(tOff), i32ptr(tIdx), nil, nil,
+			C.gorse_b200_progress_ptr(), unsafe.Pointer(&h), &res)
 	}
 	if err := b200Error(st); err != nil {
 		log.Logger().Error("gorse_b200 fit", zap.Error(err))
@@ -183,22 +173,12 @@ func fitB200(ctx context.Context, base *BaseMatrixFactorization, als bool, param
 		return Score{}
 	}
 	// host mirror: Predict == floats.Dot(GetUserFactor, GetItemFactor) bit for bit (model_test.go:53-54)
-	pm, err := newPinnedMatrix(nUsers, d)
-	if err != nil {
-		log.Logger().Error("gorse_b200 host_alloc", zap.Error(err))
-		return Score{}
-	}
-	qm, err := newPinnedMatrix(nItems, d)
-	if err != nil {
-		log.Logger().Error("gorse_b200 host_alloc", zap.Error(err))
-		return Score{}
-	}
-	if err := b200Error(C.gorse_b200_cf_get_factors(cf, pm.cptr(), qm.cptr())); err != nil {
+	pFlat, pRows := newFlatMatrix(nUsers, d)
+	qFlat, qRows := newFlatMatrix(nItems, d)
+	if err := b200Error(C.gorse_b200_cf_get_factors(cf, f32ptr(pFlat), f32ptr(qFlat))); err != nil {
 		log.Logger().Error("gorse_b200 get_factors", zap.Error(err))
 		return Score{}
 	}
-	base.UserFactor, base.ItemFactor = pm.rows, qm.rows
-	runtime.KeepAlive(pm)
-	runtime.KeepAlive(qm)
+	base.UserFactor, base.ItemFactor = pRows, qRows
 	return Score{NDCG: float32(res.ndcg), Precision: float32(res.precision), Recall: float32(res.recall)}
 }

@@ -280,27 +280,15 @@ class BruteforceIndex:
         check(lib.gorse_b200_index_len(self.h, C.byref(n)))
         return n.value
 
-    # test hooks (not part of the public header)
-    def debug_fallback_rows(self):
-        n = C.c_int64(0)
-        raw = C.CDLL(_lib.LIB_PATH)
-        raw.gorse_b200_debug_topk_fallback_rows.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
-        check(raw.gorse_b200_debug_topk_fallback_rows(self.h, C.byref(n)))
-        return n.value
+    def stage1_stats(self):
+        """(device ms, algorithmic flop, fallback rows) of the tcgen05 candidate sweep since the last call."""
+        ms, fl, fb = C.c_double(0), C.c_double(0), C.c_int64(0)
+        check(lib.gorse_b200_index_stats(self.h, C.byref(ms), C.byref(fl), C.byref(fb)))
+        return ms.value, fl.value, fb.value
 
-    def debug_stage1(self):
-        """(device ms, algorithmic flop) of the tcgen05 stage-1 kernel since the last call."""
-        ms, fl = C.c_double(0), C.c_double(0)
-        raw = C.CDLL(_lib.LIB_PATH)
-        raw.gorse_b200_debug_topk_stage1.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        check(raw.gorse_b200_debug_topk_stage1(self.h, C.byref(ms), C.byref(fl)))
-        return ms.value, fl.value
-
-    def debug_stage1_scores(self, q0, q1):
+    def stage1_scores(self, q0, q1):
         out = np.zeros((q1 - q0, len(self)), np.float32)
-        raw = C.CDLL(_lib.LIB_PATH)
-        raw.gorse_b200_debug_topk_scores.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]
-        check(raw.gorse_b200_debug_topk_scores(self.h, q0, q1, ptr(out)))
+        check(lib.gorse_b200_index_stage1_scores(self.h, q0, q1, ptr(out)))
         return out
 
     def _out(self, nq, k):

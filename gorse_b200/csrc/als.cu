@@ -15,9 +15,7 @@
 //     per-f column walk conflict-free), the running predictions live in registers.
 // In all forms sums over the row's feedback are taken lane-parallel, so results differ from the reference's serial
 // order by reassociation only (parity budget 1e-4 relative, observed ~1e-6).
-#include <algorithm>
-
-#include "cf.cuh"
+#include "als.cuh"
 
 namespace gb {
 
@@ -568,23 +566,17 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
 }
 
 // rows bucketed by length, one launch per class:
-//   lane-group form (d % 32 == 0, d <= 128; als_rows_group_kernel):  n <= 8 | n <= 16 | n <= 32 | n <= 96 | longer -> Gram form
-//                                                   (GORSE_B200_ALS_G16=0:  n <= 8 | n <= 32 | n <= 96)
-//   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp) | - |
+//   d % 32 == 0, d <= 128:  n <= 4 | n <= 8 | n <= 16  one THREAD per row (als_thread.cu)
+//                           n <= 32 (16 lanes per row) | n <= 96 (a warp per row)  lane-group form (als_rows_group_kernel)
+//                           longer -> Gram form
+//   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp)
 //   longer -> Gram form when d <= 128, else gathered from L2 without staging
 static const int kStageFloats[2] = {3072, 12288};
-#define GB_ALS_LONG 4   // index of the long-row class
-// lane-group classes: rows up to max_n entries run with G lanes per row and E entries per lane
-struct GroupClass { int max_n, G, E; };
-static const GroupClass kGroupWide[4] = {{8, 8, 1}, {32, 32, 1}, {96, 32, 3}, {0, 0, 0}};
-static const GroupClass kGroupFine[4] = {{8, 8, 1}, {16, 16, 1}, {32, 16, 2}, {96, 32, 3}};
-// default: 9..32-entry rows share a warp two by two (16 lanes each): 2.5 instead of 6 shuffles per row and coordinate,
-// 33.7 vs 43-47 ms/epoch at C3.  GORSE_B200_ALS_G16=0 gives such rows a whole warp each (A/B runs).
-static const GroupClass *group_classes()
-{
-    static const GroupClass *t = [] { const char *e = getenv("GORSE_B200_ALS_G16"); return e && atoi(e) == 0 && *e == '0' ? kGroupWide : kGroupFine; }();
-    return t;
-}
+#define GB_ALS_CLASSES 6
+#define GB_ALS_LONG 5   // index of the long-row class
+// kind 0: thread per row (max_n entries); kind 1: lane group of G lanes, E entries per lane
+struct RowClass { int max_n, kind, G, E; };
+static const RowClass kRowClasses[GB_ALS_LONG] = {{4, 0, 0, 0}, {8, 0, 0, 0}, {16, 0, 0, 0}, {32, 1, 16, 2}, {96, 1, 32, 3}};
 
 static bool als_grouped(const gorse_b200_cf *cf) { return cf->d % 32 == 0 && cf->d <= 128; }
 
@@ -603,7 +595,7 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     for (int side = 0; side < 2; side++) {
         // host offsets hold this rank's rows only, rebased: row r sits at index r - r_lo
         const int64_t *off = (side == 0 ? cf->h_user_off : cf->h_item_off).data();
-        std::vector<int32_t> cls[5];
+        std::vector<int32_t> cls[GB_ALS_CLASSES];
         // multi-rank: this rank updates its own range of users and of items only
         int32_t r_lo = 0, r_hi = 0;
         shard_range(cf, side, r_lo, r_hi);
@@ -612,13 +604,12 @@ static int32_t prepare_als(gorse_b200_cf *cf)
             int64_t n = off[(size_t)r + 1] - off[r];
             int k;
             if (grouped) {
-                const GroupClass *gc = group_classes();
                 k = GB_ALS_LONG;
-                for (int q = 0; q < 4; q++) if (gc[q].G && n <= gc[q].max_n) { k = q; break; }
+                for (int q = 0; q < GB_ALS_LONG; q++) if (n <= kRowClasses[q].max_n) { k = q; break; }
             } else k = n * dp <= kStageFloats[0] ? 0 : n * dp <= kStageFloats[1] ? 1 : GB_ALS_LONG;
             cls[k].push_back(r);
         }
-        for (int k = 0; k < 5; k++) {
+        for (int k = 0; k < GB_ALS_CLASSES; k++) {
             // longest rows first inside a class: better tail behaviour
             std::stable_sort(cls[k].begin(), cls[k].end(), [&](int32_t a, int32_t b) {
                 return off[(size_t)a + 1] - off[a] > off[(size_t)b + 1] - off[b];
@@ -686,22 +677,13 @@ static int32_t launch_group_b(gorse_b200_cf *cf, float *X, const float *Y, const
     return GORSE_B200_OK;
 }
 
-// coordinates resolved per butterfly: 1 by default.  GORSE_B200_ALS_BLOCK=4 resolves four per butterfly (10 interleaved
-// reductions, a 4x shorter dependent chain) -- measured SLOWER at C3 (72 vs 43 ms/epoch): the row kernels are bound by
-// shuffle/shared-memory issue (the LSU pipe), not by the chain's latency, and the blocked form executes 13.5 instead of 6
-// shuffles per coordinate.  Kept for A/B runs.
-static int als_block()
-{
-    static int b = [] { const char *e = getenv("GORSE_B200_ALS_BLOCK"); return e && atoi(e) == 4 ? 4 : 1; }();
-    return b;
-}
-
+// (Resolving four coordinates per shuffle butterfly -- B = 4 -- was measured SLOWER at C3 in round 1, 72 vs 43 ms/epoch:
+// the lane-group kernels are bound by shuffle / shared-memory issue, not by the latency of the dependent chain.)
 template <int G, int E, int KPL>
 static int32_t launch_group(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
                             const int32_t *rows, int32_t n_rows)
 {
-    if (als_block() == 1) return launch_group_b<G, E, KPL, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows);
-    return launch_group_b<G, E, KPL, 4>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+    return launch_group_b<G, E, KPL, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows);
 }
 
 template <int G, int E>
@@ -721,7 +703,7 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
 {
     gorse_b200_ctx *c = cf->ctx;
     const bool grouped = als_grouped(cf);
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < GB_ALS_CLASSES; k++) {
         int32_t n_rows = cf->als_rows_n[side][k];
         if (n_rows == 0) continue;
         const int32_t *rows = cf->als_rows[side][k].p;
@@ -744,11 +726,9 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             continue;
         }
         if (grouped && k != GB_ALS_LONG) {
-            const GroupClass gc = group_classes()[k];
-            if (gc.G == 8) GB_TRY((launch_group_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-            else if (gc.G == 16 && gc.E == 1) GB_TRY((launch_group_d<16, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-            else if (gc.G == 16) GB_TRY((launch_group_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-            else if (gc.E == 1) GB_TRY((launch_group_d<32, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            const RowClass rc = kRowClasses[k];
+            if (rc.kind == 0) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
+            else if (rc.G == 16) GB_TRY((launch_group_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else GB_TRY((launch_group_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             continue;
         }

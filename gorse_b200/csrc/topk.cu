@@ -426,29 +426,24 @@ int32_t gorse_b200_index_search_range(gorse_b200_index *ix, int64_t q0, int64_t 
     return search_common(ix, nullptr, nullptr, q0, q1 - q0, k, prune0, idx_out, dist_out, count_out);
 }
 
-// ---- test hooks (not part of include/gorse_b200.h) -------------------------------------------------------
-// rows of the searches since the last call that fell back to the exact scan
-int32_t gorse_b200_debug_topk_fallback_rows(gorse_b200_index *ix, int64_t *rows)
+// ---- measurement / test hooks (declared in include/gorse_b200.h) ----------------------------------------
+// since the last call: device time and algorithmic flop (2 * nq * N * d) of the stage-1 tensor-core kernel, and the rows
+// that fell back to the exact scan
+int32_t gorse_b200_index_stats(gorse_b200_index *ix, double *stage1_ms, double *stage1_flop, int64_t *fallback_rows)
 {
-    GB_CHECK_ARG(ix != nullptr && rows != nullptr, "NULL argument");
-    *rows = ix->last_fallback_rows;
-    ix->last_fallback_rows = 0;
-    return GORSE_B200_OK;
-}
-
-// device time and algorithmic flop (2 * nq * N * d) of the stage-1 tensor-core kernel since the last call
-int32_t gorse_b200_debug_topk_stage1(gorse_b200_index *ix, double *ms, double *flop)
-{
-    GB_CHECK_ARG(ix != nullptr && ms != nullptr && flop != nullptr, "NULL argument");
-    *ms = ix->stage1_ms;
-    *flop = ix->stage1_flop;
+    GB_CHECK_ARG(ix != nullptr, "ix is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (stage1_ms) *stage1_ms = ix->stage1_ms;
+    if (stage1_flop) *stage1_flop = ix->stage1_flop;
+    if (fallback_rows) *fallback_rows = ix->last_fallback_rows;
     ix->stage1_ms = ix->stage1_flop = 0.0;
+    ix->last_fallback_rows = 0;
     return GORSE_B200_OK;
 }
 
 // dense stage-1 (tensor core) scores of stored vectors [q0, q1) against all vectors, in ORIGINAL column order:
 // out[(q - q0) * n + x].  Small problems only.
-int32_t gorse_b200_debug_topk_scores(gorse_b200_index *ix, int64_t q0, int64_t q1, float *out)
+int32_t gorse_b200_index_stage1_scores(gorse_b200_index *ix, int64_t q0, int64_t q1, float *out)
 {
     GB_CHECK_ARG(ix != nullptr && out != nullptr, "NULL argument");
     std::lock_guard<std::mutex> lk(ix->mu);

@@ -253,6 +253,13 @@ int32_t gorse_b200_index_search_indices(gorse_b200_index *ix, const int64_t *q_i
  * (what logics.item_to_item asks its vector store for, logics/item_to_item.go:50-62) */
 int32_t gorse_b200_index_search_range(gorse_b200_index *ix, int64_t q0, int64_t q1, int32_t k, int32_t prune0,
                                       int32_t *idx_out, float *dist_out, int32_t *count_out);
+/* measurement hook (bench.py), like gorse_b200_ctx_timer_*: since the previous call, the device time (ms) and algorithmic
+ * flop (2 nq N d) of the tcgen05 candidate sweep, and the number of query rows that were redone by the exact scan because
+ * their candidate set could not be certified.  Any pointer may be NULL. */
+int32_t gorse_b200_index_stats(gorse_b200_index *ix, double *stage1_ms, double *stage1_flop, int64_t *fallback_rows);
+/* test hook: the dense tensor-core scores of stored vectors [q0, q1) against all N vectors, original column order,
+ * out[(q - q0) * N + x] (what the candidate sweep thresholds; small problems only) */
+int32_t gorse_b200_index_stage1_scores(gorse_b200_index *ix, int64_t q0, int64_t q1, float *out);
 
 
 /* ------------------------------------------------------------------------------------------

@@ -71,6 +71,7 @@ def _sig(L):
     L.gbo_bpr_apply_triples.argtypes = [F32, F32, C.c_int32, I32, C.c_int64, C.c_float, C.c_float]
     L.gbo_bpr_sample_triples.argtypes = [C.c_int32, I64, I32, I32, C.c_int32, C.c_uint64, C.c_int64, C.c_int64, I32]
     L.gbo_sample_user_negatives.argtypes = [C.c_int32, C.c_int32, C.c_int32, I64, I32, I64, I32, C.c_int32, C.c_uint64, I64, C.c_void_p]
+    L.gbo_fill_normal_interleaved.argtypes = [F32, C.c_int64, C.c_float, C.c_uint64, C.c_int32]
     L.gbo_bpr_epoch_threads.restype = C.c_double
     L.gbo_bpr_epoch_threads.argtypes = [F32, F32, C.c_int32, C.c_int32, I64, I32, I32, C.c_int32, C.c_uint64,
                                         C.c_int64, C.c_float, C.c_float, C.c_int32, C.c_int32]
@@ -171,6 +172,13 @@ def sample_user_negatives(n_items, train_off, train_items, test_off, test_items,
     items = np.zeros(int(off[-1]), np.int32)
     lib().gbo_sample_user_negatives(*a, off, items.ctypes.data_as(C.c_void_p))
     return off, items
+
+
+def fill_normal_interleaved(shape, std, seed, n_threads):
+    """N(0, std) table whose pages are first touched round-robin by the pinned worker threads (NUMA-interleaved)."""
+    a = np.empty(shape, np.float32)
+    lib().gbo_fill_normal_interleaved(a.reshape(-1), a.size, std, seed, n_threads)
+    return a
 
 
 def bpr_epoch_threads(P, Q, user_off, user_items, active, seed, n_steps, lr, reg, n_threads, use_ref=False):

@@ -11,6 +11,7 @@
 #include "gorse_oracle.h"
 #include <dlfcn.h>
 #include <math.h>
+#include <sched.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -566,6 +567,68 @@ void gbo_sample_user_negatives(int32_t n_items, int32_t n_users, int32_t u_base,
     }
 }
 
+/* ---- CPU-arm reproducibility (the Hogwild baseline moved 6 -> 27 M triples/s between runs): worker t is
+ * pinned to the t-th CPU of the process's affinity mask, and the factor tables can be first-touched page-interleaved
+ * over the workers so that the random row accesses spread over all NUMA nodes instead of the allocating thread's. */
+static cpu_set_t g_aff;
+static int g_aff_n = -1;
+static void aff_init(void)
+{
+    if (g_aff_n >= 0) return;
+    CPU_ZERO(&g_aff);
+    g_aff_n = sched_getaffinity(0, sizeof(g_aff), &g_aff) == 0 ? CPU_COUNT(&g_aff) : 0;
+}
+static void pin_self(int t)
+{
+    if (g_aff_n <= 0) return;
+    int want = t % g_aff_n, seen = 0;
+    for (int c = 0; c < CPU_SETSIZE; c++) {
+        if (!CPU_ISSET(c, &g_aff)) continue;
+        if (seen++ == want) {
+            cpu_set_t one;
+            CPU_ZERO(&one);
+            CPU_SET(c, &one);
+            pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+            return;
+        }
+    }
+}
+typedef struct { float *buf; int64_t n; float std; uint64_t base; int t, nt; } fill_job;
+static void *fill_worker(void *arg)
+{
+    fill_job *jb = (fill_job *)arg;
+    pin_self(jb->t);
+    const int64_t page = 1024;   /* floats per 4 KB page */
+    for (int64_t p0 = (int64_t)jb->t * page; p0 < jb->n; p0 += (int64_t)jb->nt * page) {
+        const int64_t p1 = p0 + page < jb->n ? p0 + page : jb->n;
+        for (int64_t i = p0; i < p1; i += 2) {
+            /* Box-Muller on the counter RNG: a pair of N(0, std) per counter */
+            uint64_t z = mix64(jb->base + (uint64_t)i);
+            float u1 = ((float)(uint32_t)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);
+            float u2 = ((float)(uint32_t)((z >> 8) & 0xffffff) + 0.5f) * (1.0f / 16777216.0f);
+            float r = sqrtf(-2.0f * logf(u1)) * jb->std;
+            jb->buf[i] = r * cosf(6.2831853f * u2);
+            if (i + 1 < p1) jb->buf[i + 1] = r * sinf(6.2831853f * u2);
+        }
+    }
+    return NULL;
+}
+void gbo_fill_normal_interleaved(float *buf, int64_t n, float std, uint64_t seed, int32_t n_threads)
+{
+    aff_init();
+    if (n_threads < 1) n_threads = 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    fill_job *jobs = (fill_job *)malloc(sizeof(fill_job) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; t++) {
+        fill_job jb = {buf, n, std, mix64(seed ^ 0x3c6ef372fe94f82bull), t, n_threads};
+        jobs[t] = jb;
+        pthread_create(&th[t], NULL, fill_worker, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+    free(th);
+    free(jobs);
+}
+
 static double now_sec(void)
 {
     struct timespec ts;
@@ -582,12 +645,13 @@ typedef struct {
     uint64_t base;
     int64_t s0, s1;
     float lr, reg;
-    int use_ref;
+    int use_ref, tid;
 } bpr_job;
 
 static void *bpr_worker(void *arg)
 {
     bpr_job *jb = (bpr_job *)arg;
+    pin_self(jb->tid);
     float *scratch = (float *)malloc(sizeof(float) * 4 * (size_t)jb->d);
     for (int64_t s = jb->s0; s < jb->s1; s++) {
         int32_t t[3];
@@ -616,10 +680,11 @@ double gbo_bpr_epoch_threads(float *P, float *Q, int32_t n_items, int32_t d,
     pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
     bpr_job *jobs = (bpr_job *)malloc(sizeof(bpr_job) * (size_t)n_threads);
     uint64_t base = mix64(seed);
+    aff_init();
     double t0 = now_sec();
     for (int t = 0; t < n_threads; t++) {
         bpr_job jb = {P, Q, n_items, d, user_off, user_items, active_users, n_active, base,
-                      n_steps * t / n_threads, n_steps * (t + 1) / n_threads, lr, reg, use_ref_kernels};
+                      n_steps * t / n_threads, n_steps * (t + 1) / n_threads, lr, reg, use_ref_kernels, t};
         jobs[t] = jb;
         pthread_create(&th[t], NULL, bpr_worker, &jobs[t]);
     }

@@ -68,6 +68,8 @@ void gbo_bpr_sample_triples(int32_t n_items, const int64_t *user_off, const int3
 void gbo_sample_user_negatives(int32_t n_items, int32_t n_users, int32_t u_base, const int64_t *train_off, const int32_t *train_items,
                                const int64_t *test_off, const int32_t *test_items, int32_t n_cand, uint64_t seed,
                                int64_t *neg_off_out, int32_t *neg_items_out);
+/* CPU-arm hygiene: N(0, std) fill, first-touched page-interleaved by pinned workers */
+void gbo_fill_normal_interleaved(float *buf, int64_t n, float std, uint64_t seed, int32_t n_threads);
 double gbo_bpr_epoch_threads(float *P, float *Q, int32_t n_items, int32_t d,
                              const int64_t *user_off, const int32_t *user_items,
                              const int32_t *active_users, int32_t n_active,

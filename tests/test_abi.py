@@ -118,6 +118,28 @@ def test_go_shim_only_calls_declared_entry_points():
     assert not missing, missing
 
 
+def test_go_shim_memory_rules():
+    """Lint by inspection (the shim cannot be compiled here).  (1) No C allocation may be turned into a Go slice
+    (unsafe.Slice / (*[n]T)(ptr)[:]) in a file that also frees it from a finalizer: round 1 stored rows of a cudaHostAlloc
+    buffer in the model while a finalizer could free it.  (2) A cgo.Handle travels as unsafe.Pointer(&h), never
+    unsafe.Pointer(h) (go vet / cgocheck).  (3) C functions are called directly, not through Go function values.
+    (4) every method of a finalizer-owning type keeps the receiver alive across its C calls."""
+    for dp, _, files in os.walk(os.path.join(ROOT, "go")):
+        for f in files:
+            if not f.endswith(".go"):
+                continue
+            txt = open(os.path.join(dp, f)).read()
+            code = re.sub(r"//[^\n]*", "", txt)
+            if "SetFinalizer" in code:
+                assert "unsafe.Slice(" not in code and not re.search(r"\(\*\[[^\]]*\][^)]*\)\(", code), f"{f}: C memory escapes as a slice next to a finalizer"
+                recv = re.search(r"SetFinalizer\((\w+), func\(\w+ \*(\w+)\)", code)
+                assert recv, f
+                for m in re.finditer(r"func \((\w+) \*%s\) (\w+)\([^\n]*\{\n([^\n]*)" % recv.group(2), code):
+                    assert "runtime.KeepAlive(%s)" % m.group(1) in m.group(3), f"{f}: method {m.group(2)} does not keep the receiver alive"
+            assert not re.search(r"unsafe\.Pointer\(h\)", code), f"{f}: cgo.Handle passed by value as a pointer"
+            assert not re.search(r":?=\s*C\.gorse_b200_\w+\s*$", code, flags=re.M), f"{f}: C function used as a Go value"
+
+
 def test_public_header_is_plain_c(tmp_path):
     """The boundary is a C ABI: the header must compile as C99 (what cgo feeds it to) and as C++11, warnings as errors."""
     import shutil

@@ -47,7 +47,7 @@ def test_stage1_scores_match_bf16_matmul(gb, ctx, metric, d):
     gm = gb.METRIC_EUCLIDEAN if metric == "euclid" else gb.METRIC_NEG_DOT
     with gb.BruteforceIndex(ctx, d, gm) as ix:
         ix.add(X)
-        got = ix.debug_stage1_scores(100, 400)
+        got = ix.stage1_scores(100, 400)
     Xb = bf16_round(X).astype(np.float64)
     want = Xb[100:400] @ Xb.T
     if metric == "euclid":
@@ -72,7 +72,7 @@ def test_tensor_path_equals_oracle(gb, orc, ctx, metric, d, k):
     with gb.BruteforceIndex(ctx, d, gm) as ix:
         ix.add(X)
         idx, dist, cnt = ix.search_range(1000, 1000 + NQ, k)       # all-pairs form (self excluded)
-        fb = ix.debug_fallback_rows()
+        fb = ix.stage1_stats()[2]
         qv = rng.standard_normal((128, d)).astype(np.float32)
         idx2, dist2, cnt2 = ix.search_vectors(qv, k, prune0=(metric == "euclid"))
     assert fb <= 3, f"{fb} of {NQ} rows needed the exact fallback"
