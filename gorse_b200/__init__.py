@@ -10,7 +10,8 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import (GorseB200Error, METRIC_EUCLIDEAN, METRIC_NEG_DOT, ORDER_HOGWILD, ORDER_SEQUENTIAL,  # noqa: F401
+from ._lib import (DISTANCE_COSINE, DISTANCE_DOT, DISTANCE_EUCLIDEAN, GorseB200Error, METRIC_COSINE, METRIC_EUCLIDEAN,  # noqa: F401
+                   METRIC_NEG_DOT, ORDER_HOGWILD, ORDER_SEQUENTIAL,
                    SCATTER_ATOMIC, SCATTER_STORE, check, lib, ptr)
 
 __all__ = ["Context", "CFModel", "BruteforceIndex", "GorseB200Error", "csr_from_lists", "device_count"]
@@ -361,6 +362,92 @@ class SparseIndex:
         idx, dot, cnt = np.full((nq, k), -1, np.int32), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
         check(lib.gorse_b200_sparse_index_search_range(self.h, q0, q1, k, ptr(idx), ptr(dot), ptr(cnt)))
         return idx, dot, cnt
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+class VectorCollection:
+    """One collection of a vectors.Database on the GPU (gorse_b200_vecdb_*; storage/vectors/database.go:107-120).  Works on
+    slots and int category ids; the Go shim keeps the id / category string maps."""
+
+    def __init__(self, ctx, dim, distance):
+        self.ctx, self.dim, self.distance = ctx, dim, distance
+        h = C.c_void_p()
+        check(lib.gorse_b200_vecdb_create(ctx.h, dim, distance, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib.gorse_b200_vecdb_destroy(self.h)
+            self.h = None
+
+    def count(self):
+        live, slots = C.c_int64(0), C.c_int64(0)
+        check(lib.gorse_b200_vecdb_count(self.h, C.byref(live), C.byref(slots)))
+        return live.value, slots.value
+
+    def add(self, values=None, sparse=None, hidden=None, timestamps=None, categories=None, replace=None):
+        """dense: values [n, dim]; sparse: list of (indices, values).  categories: list of int lists.  Returns the first slot."""
+        sp_off = sp_ind = None
+        if self.dim > 0:
+            values = np.ascontiguousarray(values, np.float32).reshape(-1, self.dim)
+            n = values.shape[0]
+        else:
+            n = len(sparse)
+            sp_off = np.concatenate([[0], np.cumsum([len(v[0]) for v in sparse])]).astype(np.int64)
+            sp_ind = np.ascontiguousarray(np.concatenate([np.asarray(v[0], np.uint32) for v in sparse]) if n else np.zeros(0), np.uint32)
+            values = np.ascontiguousarray(np.concatenate([np.asarray(v[1], np.float32) for v in sparse]) if n else np.zeros(0), np.float32)
+        hid = None if hidden is None else np.ascontiguousarray(hidden, np.uint8)
+        ts = None if timestamps is None else np.ascontiguousarray(timestamps, np.int64)
+        co = cv = None
+        if categories is not None:
+            co = np.concatenate([[0], np.cumsum([len(c) for c in categories])]).astype(np.int64)
+            cv = np.ascontiguousarray([x for c in categories for x in c], np.int32)
+        rep = None if replace is None else np.ascontiguousarray(replace, np.int64)
+        first = C.c_int64(0)
+        check(lib.gorse_b200_vecdb_add(self.h, n, ptr(values), ptr(sp_off), ptr(sp_ind), ptr(hid), ptr(ts), ptr(co), ptr(cv), ptr(rep), C.byref(first)))
+        return first.value
+
+    def get(self, slots):
+        slots = np.ascontiguousarray(slots, np.int64)
+        n = slots.size
+        vals = np.zeros((n, max(self.dim, 1)), np.float32)
+        hid, ts, live = np.zeros(n, np.uint8), np.zeros(n, np.int64), np.zeros(n, np.uint8)
+        check(lib.gorse_b200_vecdb_get(self.h, ptr(slots), n, ptr(vals) if self.dim > 0 else None, ptr(hid), ptr(ts), ptr(live)))
+        return vals, hid, ts, live
+
+    def get_sparse(self, slot, cap=4096):
+        ind, val, nnz = np.zeros(cap, np.uint32), np.zeros(cap, np.float32), C.c_int32(0)
+        check(lib.gorse_b200_vecdb_get_sparse(self.h, slot, ptr(ind), ptr(val), cap, C.byref(nnz)))
+        return ind[:nnz.value], val[:nnz.value]
+
+    def delete_before(self, timestamp_ms, cap=1 << 20):
+        out, cnt = np.zeros(cap, np.int64), C.c_int64(0)
+        check(lib.gorse_b200_vecdb_delete_before(self.h, timestamp_ms, ptr(out), cap, C.byref(cnt)))
+        return out[:min(cnt.value, cap)]
+
+    def query(self, q, categories=(), topk=10):
+        """q: dense [nq, dim] array, or a list of (indices, values) for a sparse collection.
+        -> (slots int64 [nq, topk], scores float32 [nq, topk], count int32 [nq])"""
+        sp_off = sp_ind = None
+        if self.dim > 0:
+            qv = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+            nq = qv.shape[0]
+        else:
+            nq = len(q)
+            sp_off = np.concatenate([[0], np.cumsum([len(v[0]) for v in q])]).astype(np.int64)
+            sp_ind = np.ascontiguousarray(np.concatenate([np.asarray(v[0], np.uint32) for v in q]), np.uint32)
+            qv = np.ascontiguousarray(np.concatenate([np.asarray(v[1], np.float32) for v in q]), np.float32)
+        cats = np.ascontiguousarray(list(categories), np.int32)
+        k = max(topk, 1)
+        slots, scores, cnt = np.full((nq, k), -1, np.int64), np.zeros((nq, k), np.float32), np.zeros(nq, np.int32)
+        check(lib.gorse_b200_vecdb_query(self.h, nq, ptr(qv), ptr(sp_off), ptr(sp_ind), ptr(cats) if cats.size else None, cats.size, topk,
+                                         ptr(slots), ptr(scores), ptr(cnt)))
+        return slots, scores, cnt
 
     def __enter__(self):
         return self

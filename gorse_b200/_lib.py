@@ -17,7 +17,8 @@ ERR_ARG, ERR_CUDA, ERR_NCCL, ERR_OOM, ERR_RANGE, ERR_STATE, ERR_UNSUPPORTED = -1
 
 SCATTER_STORE, SCATTER_ATOMIC = 0, 1
 ORDER_HOGWILD, ORDER_SEQUENTIAL = 0, 1
-METRIC_EUCLIDEAN, METRIC_NEG_DOT = 0, 1
+METRIC_EUCLIDEAN, METRIC_NEG_DOT, METRIC_COSINE = 0, 1, 2
+DISTANCE_COSINE, DISTANCE_EUCLIDEAN, DISTANCE_DOT = 0, 1, 2   # vectors.Distance
 
 
 def _nd(dt):
@@ -83,6 +84,14 @@ PROTOTYPES = {
     "gorse_b200_sparse_index_add": (C.c_int32, [VP, VP, VP, VP, C.c_int64, C.POINTER(C.c_int64)]),
     "gorse_b200_sparse_index_len": (C.c_int32, [VP, C.POINTER(C.c_int64)]),
     "gorse_b200_sparse_index_search_range": (C.c_int32, [VP, C.c_int64, C.c_int64, C.c_int32, VP, VP, VP]),
+    "gorse_b200_vecdb_create": (C.c_int32, [VP, C.c_int32, C.c_int32, PVP]),
+    "gorse_b200_vecdb_destroy": (C.c_int32, [VP]),
+    "gorse_b200_vecdb_count": (C.c_int32, [VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "gorse_b200_vecdb_add": (C.c_int32, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, C.POINTER(C.c_int64)]),
+    "gorse_b200_vecdb_get": (C.c_int32, [VP, VP, C.c_int64, VP, VP, VP, VP]),
+    "gorse_b200_vecdb_get_sparse": (C.c_int32, [VP, C.c_int64, VP, VP, C.c_int32, C.POINTER(C.c_int32)]),
+    "gorse_b200_vecdb_delete_before": (C.c_int32, [VP, C.c_int64, VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "gorse_b200_vecdb_query": (C.c_int32, [VP, C.c_int64, VP, VP, VP, VP, C.c_int32, C.c_int32, VP, VP, VP]),
 }
 
 

@@ -4,9 +4,10 @@
 // Why this shape (round 2; the lane-group kernel it replaces ran at sm__warps_active 12 %, 0.054 of the HBM roofline):
 //   * the coordinate sweep over f is strictly sequential per row, but rows are independent: a thread owns a row, so the
 //     sweep needs NO shuffle and NO reduction -- a warp advances 32 rows per instruction instead of 2-4;
-//   * x (the row being solved, D floats) lives in REGISTERS: the f loop is fully unrolled, every x[k] is a named register
-//     and the S-term  b_f = w * sum_{k != f} x_k S_kf  is D-1 FMAs whose second operand is a warp-uniform (broadcast) shared
-//     memory read of row f of S (S is symmetric);
+//   * x (the row being solved, D floats) lives in REGISTERS, every x[k] a named register, and the S-term
+//     b_f = w * sum_{k != f} x_k S_kf  is D FMAs whose second operand is a warp-uniform (broadcast) shared-memory read of
+//     row f of S (S is symmetric).  The f loop is ROLLED (4 coordinates per iteration): the one dynamically indexed read /
+//     write of x per coordinate goes through a local-memory copy, the register copy is refreshed by predicated moves;
 //   * the gathered opposite-table rows Y[R_x] are needed one COLUMN at a time.  Each warp stages, for a block of BC
 //     coordinates, the BC-float slice of every entry of its 32 rows into shared memory with warp-cooperative 128-bit
 //     loads (BC/4 lanes per entry: whole 32..128-byte segments of a row, 1/8 .. 1/2 of the L1 wavefronts a thread-per-row
@@ -50,6 +51,10 @@ __device__ __forceinline__ void stage_block(float *ys, const float *Y, const int
     }
 }
 
+// BCU coordinates are unrolled inside the (rolled) sweep loop.  The first version unrolled all D coordinates (600 KB of
+// straight-line code at D = 128, five minutes of ptxas) and was no faster (profiles/r02_als_thread.md).
+#define GB_ALS_BCU 4
+
 template <int D, int NMAX, int BC, int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, 1)
 als_thread_kernel(float *X, const float *Y, const int64_t *off, const int32_t *idx, const float *S, float reg, float w,
@@ -57,6 +62,8 @@ als_thread_kernel(float *X, const float *Y, const int64_t *off, const int32_t *i
 {
     using G = StageGeom<BC>;
     constexpr int YS = NMAX * BC * G::STR;   // staging floats per warp
+    constexpr int BCU = GB_ALS_BCU;
+    static_assert(BC % BCU == 0 && D % BC == 0, "block sizes");
     extern __shared__ __align__(16) float smem[];
     float *Ss = smem;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -75,76 +82,91 @@ als_thread_kernel(float *X, const float *Y, const int64_t *off, const int32_t *i
         int32_t ids[NMAX];
 #pragma unroll
         for (int t = 0; t < NMAX; t++) ids[t] = t < n ? __ldg(idx + o + t) : 0;
-        float x[D];
+        // x twice: in registers (every x[k] a named register: the S-dot below) and in local memory (per-lane interleaved by
+        // the hardware, i.e. coalesced) for the one dynamically indexed read and write per coordinate
+        float x[D], xl[D];
 #pragma unroll
         for (int k4 = 0; k4 < D / 4; k4++) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (act) v = *(reinterpret_cast<const float4 *>(X + (int64_t)r * D) + k4);
             x[4 * k4] = v.x; x[4 * k4 + 1] = v.y; x[4 * k4 + 2] = v.z; x[4 * k4 + 3] = v.w;
+            xl[4 * k4] = v.x; xl[4 * k4 + 1] = v.y; xl[4 * k4 + 2] = v.z; xl[4 * k4 + 3] = v.w;
         }
         const int nmax = __reduce_max_sync(0xffffffffu, n);
         // ---- pass 1: pred_t = x . y_t (model.go:661-663) ----
         float pred[NMAX];
 #pragma unroll
         for (int t = 0; t < NMAX; t++) pred[t] = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < D / BC; b++) {
             __syncwarp();
             stage_block<D, NMAX, BC>(ys, Y, ids, n, nmax, b, lane);
             __syncwarp();
+#pragma unroll 4
+            for (int c = 0; c < BC; c++) {
+                const float xf = xl[b * BC + c];
+                const float *yc = ys + c * G::STR + lane;
 #pragma unroll
-            for (int t = 0; t < NMAX; t++) {
-                if (t >= nmax) break;
-                if (t < n) {
-#pragma unroll
-                    for (int c = 0; c < BC; c++) pred[t] = fmaf(x[b * BC + c], ys[(t * BC + c) * G::STR + lane], pred[t]);
+                for (int t = 0; t < NMAX; t++) {
+                    if (t >= nmax) break;
+                    if (t < n) pred[t] = fmaf(xf, yc[t * BC * G::STR], pred[t]);
                 }
             }
         }
         // ---- pass 2: the coordinate sweep (model.go:664-686) ----
-#pragma unroll
+#pragma unroll 1
         for (int b = 0; b < D / BC; b++) {
             __syncwarp();
             stage_block<D, NMAX, BC>(ys, Y, ids, n, nmax, b, lane);
             __syncwarp();
+#pragma unroll 1
+            for (int cb = 0; cb < BC / BCU; cb++) {
+                const int fb = (b * BC) / BCU + cb;          // coordinates [fb*BCU, (fb+1)*BCU)
 #pragma unroll
-            for (int c = 0; c < BC; c++) {
-                const int f = b * BC + c;
-                const float xf = x[f];
-                float a = 0.f, cc = 0.f, yv[NMAX];
+                for (int j = 0; j < BCU; j++) {
+                    const int f = fb * BCU + j;
+                    const float xf = xl[f];
+                    const float *yc = ys + (cb * BCU + j) * G::STR + lane;
+                    float a = 0.f, cc = 0.f, yv[NMAX];
 #pragma unroll
-                for (int t = 0; t < NMAX; t++) {
-                    yv[t] = 0.f;
-                    if (t >= nmax) break;
-                    const float y = t < n ? ys[(t * BC + c) * G::STR + lane] : 0.f;
-                    yv[t] = y;
-                    const float res = pred[t] - xf * y;                 // :666-668
-                    pred[t] = res;
-                    a = a + (1.0f - omw * res) * y;                      // :672
-                    cc = cc + (omw * y) * y;                             // :673
-                }
-                // :675-679   S is symmetric: read row f (contiguous, warp-uniform) instead of column f
-                float acc[8];
+                    for (int t = 0; t < NMAX; t++) {
+                        yv[t] = 0.f;
+                        if (t >= nmax) break;
+                        const float y = t < n ? yc[t * BC * G::STR] : 0.f;
+                        yv[t] = y;
+                        const float res = pred[t] - xf * y;                 // :666-668
+                        pred[t] = res;
+                        a = a + (1.0f - omw * res) * y;                      // :672
+                        cc = cc + (omw * y) * y;                             // :673
+                    }
+                    // :675-679   b = w * sum_{k != f} x_k S_kf.  S is symmetric: row f (contiguous, warp-uniform address) instead
+                    // of column f; the k = f term is taken out afterwards (x_f S_ff is exactly what the dot added)
+                    float acc[8];
 #pragma unroll
-                for (int i = 0; i < 8; i++) acc[i] = 0.f;
-                const float4 *srow = reinterpret_cast<const float4 *>(Ss + f * D);
-                float sff = 0.f;
+                    for (int i = 0; i < 8; i++) acc[i] = 0.f;
+                    const float4 *srow = reinterpret_cast<const float4 *>(Ss + f * D);
 #pragma unroll
-                for (int k4 = 0; k4 < D / 4; k4++) {
-                    const float4 s4 = srow[k4];
-                    const int k = 4 * k4;
-                    if (k != f) acc[(2 * k4) & 7] = fmaf(x[k], s4.x, acc[(2 * k4) & 7]); else sff = s4.x;
-                    if (k + 1 != f) acc[(2 * k4 + 1) & 7] = fmaf(x[k + 1], s4.y, acc[(2 * k4 + 1) & 7]); else sff = s4.y;
-                    if (k + 2 != f) acc[(2 * k4 + 2) & 7] = fmaf(x[k + 2], s4.z, acc[(2 * k4 + 2) & 7]); else sff = s4.z;
-                    if (k + 3 != f) acc[(2 * k4 + 3) & 7] = fmaf(x[k + 3], s4.w, acc[(2 * k4 + 3) & 7]); else sff = s4.w;
-                }
-                const float bsum = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-                const float xn = __fdiv_rn(a - w * bsum, (cc + w * sff) + reg);   // :680
-                x[f] = xn;
+                    for (int k4 = 0; k4 < D / 4; k4++) {
+                        const float4 s4 = srow[k4];
+                        acc[(4 * k4) & 7] = fmaf(x[4 * k4], s4.x, acc[(4 * k4) & 7]);
+                        acc[(4 * k4 + 1) & 7] = fmaf(x[4 * k4 + 1], s4.y, acc[(4 * k4 + 1) & 7]);
+                        acc[(4 * k4 + 2) & 7] = fmaf(x[4 * k4 + 2], s4.z, acc[(4 * k4 + 2) & 7]);
+                        acc[(4 * k4 + 3) & 7] = fmaf(x[4 * k4 + 3], s4.w, acc[(4 * k4 + 3) & 7]);
+                    }
+                    const float sff = Ss[f * D + f];
+                    const float dot = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+                    const float bsum = fmaf(-xf, sff, dot);
+                    const float xn = __fdiv_rn(a - w * bsum, (cc + w * sff) + reg);   // :680
+                    xl[f] = xn;
+                    // the register copy: one predicated move per block of BCU coordinates (fb is warp-uniform)
 #pragma unroll
-                for (int t = 0; t < NMAX; t++) {
-                    if (t >= nmax) break;
-                    pred[t] = pred[t] + xn * yv[t];                      // :682-684
+                    for (int B = 0; B < D / BCU; B++)
+                        if (fb == B) x[B * BCU + j] = xn;
+#pragma unroll
+                    for (int t = 0; t < NMAX; t++) {
+                        if (t >= nmax) break;
+                        pred[t] = pred[t] + xn * yv[t];                      // :682-684
+                    }
                 }
             }
         }

@@ -15,29 +15,10 @@
 // Only rows that share a feature with the query can have a non-zero dot; rows with dot <= 0 are never returned (the
 // reference drops them right after the query, logics/item_to_item.go:73).  Roofline class: HBM/L2 (N floats scanned per query).
 #include <algorithm>
-#include <mutex>
-#include <vector>
 
-#include "common.cuh"
+#include "sparse.cuh"
 
 using namespace gb;
-
-struct gorse_b200_sparse_index {
-    gorse_b200_ctx *ctx = nullptr;
-    std::mutex mu;
-    // host copy (append-friendly); device mirrors are rebuilt lazily after an add
-    std::vector<int64_t> h_off{0};
-    std::vector<uint32_t> h_ind;
-    std::vector<float> h_val;
-    uint32_t n_features = 0;
-    bool dirty = true;
-    DevBuf<int64_t> off, foff;
-    DevBuf<uint32_t> ind;
-    DevBuf<float> val, fval;
-    DevBuf<int32_t> frow;
-    DevBuf<float> acc;
-    int64_t acc_slots = 0;
-};
 
 namespace {
 
@@ -73,19 +54,26 @@ __device__ __forceinline__ void list_insert_warp(float *ld, int32_t *li, int &le
 
 __global__ void __launch_bounds__(128)
 sparse_search_kernel(const int64_t *off, const uint32_t *ind, const float *val, const int64_t *foff, const int32_t *frow,
-                     const float *fval, int64_t N, int64_t q0, int64_t nq, int k, float *acc, int32_t *out_idx, float *out_dot,
-                     int32_t *out_count)
+                     const float *fval, int64_t N, uint32_t n_features, int64_t q0, int64_t nq, int k, float *acc, int32_t *out_idx,
+                     float *out_dot, int32_t *out_count, const int64_t *q_off, const uint32_t *q_ind, const float *q_val,
+                     const uint8_t *allow)
 {
+    // queries: stored rows q0 + q (never returned themselves), or -- q_off != nullptr -- rows of an external CSR
+    // (vecdb.cu: QueryVectors passes the vector, not its id); allow: optional per-row filter
     extern __shared__ unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float *ld = reinterpret_cast<float *>(sm_raw) + (size_t)wid * k;
     int32_t *li = reinterpret_cast<int32_t *>(reinterpret_cast<float *>(sm_raw) + (size_t)nw * k) + (size_t)wid * k;
     float *a = acc + ((int64_t)blockIdx.x * nw + wid) * N;   // this warp's accumulator row, all zero between queries
     for (int64_t q = (int64_t)blockIdx.x * nw + wid; q < nq; q += (int64_t)gridDim.x * nw) {
-        const int64_t row = q0 + q;
-        for (int64_t t = off[row]; t < off[row + 1]; t++) {
-            const uint32_t f = ind[t];
-            const float v = val[t];
+        const int64_t row = q_off ? -1 : q0 + q;
+        const int64_t tb = q_off ? q_off[q] : off[row], te = q_off ? q_off[q + 1] : off[row + 1];
+        const uint32_t *qi = q_off ? q_ind : ind;
+        const float *qv = q_off ? q_val : val;
+        for (int64_t t = tb; t < te; t++) {
+            const uint32_t f = qi[t];
+            const float v = qv[t];
+            if (f >= n_features) continue;   // a feature no stored vector has (warp-uniform)
             for (int64_t p = foff[f] + lane; p < foff[f + 1]; p += 32) {
                 const int32_t c = frow[p];
                 a[c] = a[c] + v * fval[p];        // unfused multiply and add, like the oracle (-fmad=false)
@@ -100,7 +88,7 @@ sparse_search_kernel(const int64_t *off, const uint32_t *ind, const float *val, 
                 x = a[c];
                 if (x != 0.f) a[c] = 0.f;
             }
-            const bool valid = c < N && c != row && x > 0.f;
+            const bool valid = c < N && c != row && x > 0.f && (allow == nullptr || allow[c] != 0);
             // cheap pre-filter against the current k-th best before the warp-wide insertion
             const bool cand = valid && (len < k || before(-x, (int32_t)c, ld[k - 1], li[k - 1]));
             unsigned m = __ballot_sync(0xffffffffu, cand);
@@ -239,9 +227,26 @@ int32_t gorse_b200_sparse_index_search_range(gorse_b200_sparse_index *ix, int64_
     const int64_t nq = q1 - q0;
     if (nq == 0) return GORSE_B200_OK;
     GB_CHECK_ARG(idx_out != nullptr && dot_out != nullptr && count_out != nullptr, "NULL output");
+    return gb::sparse_search_host(ix, q0, nq, nullptr, nullptr, nullptr, nullptr, k, idx_out, dot_out, count_out);
+}
+
+}  // extern "C"
+
+namespace gb {
+
+// queries = stored rows [q0, q0 + nq) (q_off == nullptr) or nq rows of a HOST CSR (q_off/q_ind/q_val); allow = optional DEVICE
+// per-row filter; results to host buffers.  The caller holds ix->mu.
+int32_t sparse_search_host(gorse_b200_sparse_index *ix, int64_t q0, int64_t nq, const int64_t *q_off, const uint32_t *q_ind,
+                           const float *q_val, const uint8_t *d_allow, int32_t k, int32_t *idx_out, float *dot_out, int32_t *count_out)
+{
+    const int64_t n = (int64_t)ix->h_off.size() - 1;
     gorse_b200_ctx *c = ix->ctx;
     ScopedDevice sd(c->device);
     GB_TRY(sync_device(ix));
+    if (n == 0) {
+        for (int64_t q = 0; q < nq; q++) count_out[q] = 0;
+        return GORSE_B200_OK;
+    }
     const int warps = 4;
     // one accumulator row per resident warp, at most ~1 GB of them
     int64_t slots = std::min<int64_t>((nq + warps - 1) / warps * warps, (int64_t)c->sm_count * 4 * warps);
@@ -252,16 +257,28 @@ int32_t gorse_b200_sparse_index_search_range(gorse_b200_sparse_index *ix, int64_
         ix->acc_slots = slots;
     }
     DevBuf<int32_t> d_idx, d_cnt;
-    DevBuf<float> d_dot;
+    DevBuf<float> d_dot, dq_val;
+    DevBuf<int64_t> dq_off;
+    DevBuf<uint32_t> dq_ind;
     int32_t st = GORSE_B200_OK;
-    auto done = [&](int32_t s) { d_idx.free(); d_cnt.free(); d_dot.free(); return s; };
+    auto done = [&](int32_t s) { cudaStreamSynchronize(c->stream); d_idx.free(); d_cnt.free(); d_dot.free(); dq_val.free(); dq_off.free(); dq_ind.free(); return s; };
     if ((st = d_idx.alloc((size_t)nq * k)) || (st = d_dot.alloc((size_t)nq * k)) || (st = d_cnt.alloc((size_t)nq))) return done(st);
+    cudaError_t e = cudaSuccess;
+    if (q_off) {
+        const int64_t qn = q_off[nq];
+        if ((st = dq_off.alloc((size_t)nq + 1)) || (st = dq_ind.alloc((size_t)qn)) || (st = dq_val.alloc((size_t)qn))) return done(st);
+        e = cudaMemcpyAsync(dq_off.p, q_off, sizeof(int64_t) * ((size_t)nq + 1), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && qn) e = cudaMemcpyAsync(dq_ind.p, q_ind, sizeof(uint32_t) * (size_t)qn, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess && qn) e = cudaMemcpyAsync(dq_val.p, q_val, sizeof(float) * (size_t)qn, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) { set_error("sparse search upload: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    }
     const int grid = (int)(slots / warps);
     const size_t sm = (size_t)warps * 2 * (size_t)k * 4;
     sparse_search_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->off.p, ix->ind.p, ix->val.p, ix->foff.p, ix->frow.p, ix->fval.p, n,
-                                                             q0, nq, k, ix->acc.p, d_idx.p, d_dot.p, d_cnt.p);
+                                                             ix->n_features, q0, nq, k, ix->acc.p, d_idx.p, d_dot.p, d_cnt.p,
+                                                             q_off ? dq_off.p : nullptr, dq_ind.p, dq_val.p, d_allow);
     c->launches++;
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * (size_t)nq * k, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dot_out, d_dot.p, sizeof(float) * (size_t)nq * k, cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(count_out, d_cnt.p, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, c->stream);
@@ -270,4 +287,4 @@ int32_t gorse_b200_sparse_index_search_range(gorse_b200_sparse_index *ix, int64_
     return done(GORSE_B200_OK);
 }
 
-}  // extern "C"
+}  // namespace gb

@@ -17,10 +17,20 @@ namespace gb {
 
 // exact distance by a quad, d % 16 == 0.  Euclidean: floats_avx512.c:374-441 (sub, mul, add: no fusing).
 __device__ __forceinline__ float quad_dist(const float4 *q /* C regs, query chunk c at q[c] */, const float *x, int chunks,
-                                           int lane4, unsigned mask, int metric)
+                                           int lane4, unsigned mask, int metric, float qq)
 {
     const float4 *x4 = reinterpret_cast<const float4 *>(x) + lane4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (metric == GORSE_B200_METRIC_COSINE) {   // 1 - q.x / (|q| |x|); the reference's arithmetic lives in its vector store (unpinned)
+        float4 xx = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < chunks; c++) {
+            const float4 b = __ldg(x4 + 4 * c);
+            dot_chunk(acc, q[c], b, c == 0);
+            dot_chunk(xx, b, b, c == 0);
+        }
+        const float dot = quad_tree(acc, mask), nx = quad_tree(xx, mask);
+        return __fsub_rn(1.0f, __fdiv_rn(dot, __fmul_rn(__fsqrt_rn(qq), __fsqrt_rn(nx))));
+    }
     if (metric == GORSE_B200_METRIC_NEG_DOT) {
         for (int c = 0; c < chunks; c++) dot_chunk(acc, q[c], __ldg(x4 + 4 * c), c == 0);
         return -quad_tree(acc, mask);
@@ -36,9 +46,11 @@ __device__ __forceinline__ float quad_dist(const float4 *q /* C regs, query chun
 }
 
 // any d, one thread (8-lane block + fused tails as in the reference)
-__device__ inline float dist_any(const float *a, const float *b, int n, int metric)
+__device__ inline float dist_any(const float *a, const float *b, int n, int metric, float qq)
 {
     if (metric == GORSE_B200_METRIC_NEG_DOT) return -dot_any(a, b, n);
+    if (metric == GORSE_B200_METRIC_COSINE)
+        return __fsub_rn(1.0f, __fdiv_rn(dot_any(a, b, n), __fmul_rn(__fsqrt_rn(qq), __fsqrt_rn(dot_any(b, b, n)))));
     int epoch = n / 16, remain = n % 16;
     float s[16];
 #pragma unroll
@@ -124,7 +136,7 @@ __global__ void __launch_bounds__(128)
 topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_ptr, const int64_t *q_idx, int64_t q0,
                   int64_t nq, int k, const int32_t *cand, const int32_t *cand_count, int cand_stride, const int32_t *row_list,
                   int32_t *out_idx, float *out_dist, int32_t *out_count, int prune0, int *nan_flag, int n_seg, int64_t seg_len,
-                  int cand_by_slot)
+                  int cand_by_slot, const uint8_t *allow /* optional per-vector filter (vecdb.cu): 0 = never returned */)
 {
     extern __shared__ unsigned char sm_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -146,6 +158,7 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
         else { self = q_idx ? q_idx[qi] : q0 + qi; qsrc = X + self * d; }
         for (int e = lane; e < d; e += 32) qs[e] = qsrc[e];
         __syncwarp();
+        const float qq = metric == GORSE_B200_METRIC_COSINE ? dot_any(qs, qs, d) : 0.f;
         int len = 0;
         const int64_t cidx = cand_by_slot ? row_slot : qi;
         const int32_t *cl = cand ? cand + cidx * cand_stride : nullptr;
@@ -161,9 +174,9 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
                 int64_t t = base + quad;
                 int64_t v = -1;
                 if (t < total) v = cl ? (int64_t)cl[t] : t;
-                bool valid = v >= 0 && v != self;
+                bool valid = v >= 0 && v != self && (allow == nullptr || allow[v] != 0);
                 float dv = 0.f;
-                if (valid) dv = quad_dist(qreg, X + v * d, chunks, lane4, qmask, metric);
+                if (valid) dv = quad_dist(qreg, X + v * d, chunks, lane4, qmask, metric, qq);
                 // lane 0 consumes the 8 quads' results in index order
                 for (int s = 0; s < 8; s++) {
                     float dd = __shfl_sync(0xffffffffu, dv, 4 * s);
@@ -182,9 +195,9 @@ topk_exact_kernel(const float *X, int64_t N, int d, int metric, const float *q_p
                 int64_t t = base + lane;
                 int64_t v = -1;
                 if (t < total) v = cl ? (int64_t)cl[t] : t;
-                bool valid = v >= 0 && v != self;
+                bool valid = v >= 0 && v != self && (allow == nullptr || allow[v] != 0);
                 float dv = 0.f;
-                if (valid) dv = dist_any(qs, X + v * d, d, metric);
+                if (valid) dv = dist_any(qs, X + v * d, d, metric, qq);
                 for (int s = 0; s < 32; s++) {
                     float dd = __shfl_sync(0xffffffffu, dv, s);
                     int64_t vv = __shfl_sync(0xffffffffu, v, s);
@@ -227,7 +240,7 @@ int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qi
     GB_CUDA(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nq + warps - 1) / warps, (int64_t)c->sm_count * 8));
     topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, nq, k, d_cand,
-                                                         d_cand_count, cand_stride, row_list, d_idx, d_dist, d_count, prune0, d_nan, 1, ix->n, 0);
+                                                         d_cand_count, cand_stride, row_list, d_idx, d_dist, d_count, prune0, d_nan, 1, ix->n, 0, nullptr);
     GB_LAUNCHED(c);
     return GORSE_B200_OK;
 }
@@ -235,7 +248,8 @@ int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qi
 // A few rows, each against ALL vectors (the tensor path's certified-fallback): split every row's scan into segments
 // handled by different warps (partial top-k per segment, no prune0 yet), then merge the partial lists exactly.
 int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int32_t n_rows, int k,
-                           const int32_t *row_list, int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan)
+                           const int32_t *row_list, int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan,
+                           const uint8_t *allow)
 {
     gorse_b200_ctx *c = ix->ctx;
     const int warps = 4;
@@ -251,11 +265,11 @@ int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t
     GB_CUDA(cudaFuncSetAttribute(topk_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int grid = (int)std::max<int64_t>(1, std::min<int64_t>((slots + warps - 1) / warps, (int64_t)c->sm_count * 16));
     topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, slots, k, nullptr, nullptr, 0,
-                                                         row_list, p_idx.p, p_dist.p, p_cnt.p, 0, d_nan, n_seg, seg_len, 0);
+                                                         row_list, p_idx.p, p_dist.p, p_cnt.p, 0, d_nan, n_seg, seg_len, 0, allow);
     c->launches++;
     grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + warps - 1) / warps, (int64_t)c->sm_count * 8));
     topk_exact_kernel<<<grid, 32 * warps, sm, c->stream>>>(ix->X.p, ix->n, ix->d, ix->metric, d_q, d_qidx, q0, n_rows, k, p_idx.p, nullptr,
-                                                         n_seg * k, row_list, d_idx, d_dist, d_count, prune0, d_nan, 1, ix->n, 1);
+                                                         n_seg * k, row_list, d_idx, d_dist, d_count, prune0, d_nan, 1, ix->n, 1, nullptr);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) { set_error("exact fallback: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
@@ -329,7 +343,8 @@ int32_t gorse_b200_index_create(gorse_b200_ctx *ctx, int32_t dim, int32_t metric
     GB_CHECK_ARG(ctx != nullptr && out != nullptr, "NULL ctx/out");
     *out = nullptr;
     GB_CHECK_ARG(dim >= 1 && dim <= 16384, "dim %d out of range", dim);
-    GB_CHECK_ARG(metric == GORSE_B200_METRIC_EUCLIDEAN || metric == GORSE_B200_METRIC_NEG_DOT, "unknown metric %d", metric);
+    GB_CHECK_ARG(metric == GORSE_B200_METRIC_EUCLIDEAN || metric == GORSE_B200_METRIC_NEG_DOT || metric == GORSE_B200_METRIC_COSINE,
+                 "unknown metric %d", metric);
     gorse_b200_index *ix = new (std::nothrow) gorse_b200_index();
     if (!ix) { set_error("host allocation failed"); return GORSE_B200_ERR_OOM; }
     ix->ctx = ctx;

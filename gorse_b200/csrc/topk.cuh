@@ -35,7 +35,8 @@ int32_t launch_exact(gorse_b200_index *ix, const float *d_q, const int64_t *d_qi
                      int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan);
 
 int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int32_t n_rows, int k,
-                           const int32_t *row_list, int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan);
+                           const int32_t *row_list, int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan,
+                           const uint8_t *allow = nullptr);
 
 bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k);
 int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,

@@ -490,6 +490,7 @@ bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k)
     if (const char *e = getenv("GORSE_B200_TOPK_EXACT")) if (*e == '1') return false;
     const int kp = kp_of(ix);
     // the sample needs >= 32 tiles to make theta tight; small problems are faster on the exact scan anyway
+    if (ix->metric != GORSE_B200_METRIC_EUCLIDEAN && ix->metric != GORSE_B200_METRIC_NEG_DOT) return false;   // cosine (vecdb.cu): exact scan
     return kp <= mma::BK * mma::MAX_KB && k >= 1 && k <= 128 && ix->n >= 32768 && nq >= 64 && ix->n < (1ll << 31);
 }
 

@@ -231,7 +231,8 @@ int32_t gorse_b200_als_fit(gorse_b200_cf *cf, const gorse_b200_fit_params *param
  * ---------------------------------------------------------------------------------------- */
 typedef enum {
     GORSE_B200_METRIC_EUCLIDEAN = 0, /* floats.Euclidean (common/ann/ann_test.go:126) */
-    GORSE_B200_METRIC_NEG_DOT = 1    /* -floats.Dot (logics/cf.go:32-34) */
+    GORSE_B200_METRIC_NEG_DOT = 1,   /* -floats.Dot (logics/cf.go:32-34) */
+    GORSE_B200_METRIC_COSINE = 2     /* 1 - cos (vector collections only, storage/vectors/database.go:30; always the exact scan) */
 } gorse_b200_metric;
 
 int32_t gorse_b200_index_create(gorse_b200_ctx *ctx, int32_t dim, int32_t metric, gorse_b200_index **out);
@@ -303,6 +304,47 @@ int32_t gorse_b200_sparse_index_len(const gorse_b200_sparse_index *ix, int64_t *
  * Feed a row to gorse_b200_similar_scores with GORSE_B200_METRIC_NEG_DOT after negating the dots. */
 int32_t gorse_b200_sparse_index_search_range(gorse_b200_sparse_index *ix, int64_t q0, int64_t q1, int32_t k, int32_t *idx_out,
                                              float *dot_out, int32_t *count_out);
+
+/* ------------------------------------------------------------------------------------------
+ * Vector collection: the GPU backend of vectors.Database (storage/vectors/database.go:107-120; semantics of the
+ * reference's default backend storage/vectors/xvec.go:288-449), registered from Go with
+ * vectors.Register([]string{"b200://"}, ...) (database.go:161-165; go/storage/vectors/b200.go).  One handle = one
+ * collection.  Vectors live in SLOTS (int64, insertion order); the shim owns the id string <-> slot map and the category
+ * string <-> int32 map.  dim = 0: sparse vectors, Dot only (xvec.go:243-248).  Thread-safe per collection.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {   /* vectors.Distance, storage/vectors/database.go:27-33 */
+    GORSE_B200_DISTANCE_COSINE = 0,
+    GORSE_B200_DISTANCE_EUCLIDEAN = 1,
+    GORSE_B200_DISTANCE_DOT = 2
+} gorse_b200_distance;
+typedef struct gorse_b200_vecdb gorse_b200_vecdb;
+int32_t gorse_b200_vecdb_create(gorse_b200_ctx *ctx, int32_t dim, int32_t distance, gorse_b200_vecdb **out); /* AddCollection */
+int32_t gorse_b200_vecdb_destroy(gorse_b200_vecdb *db);                                                     /* DeleteCollection */
+/* CountVectors (xvec.go:274-286): live vectors; *slots_out = slots ever assigned */
+int32_t gorse_b200_vecdb_count(gorse_b200_vecdb *db, int64_t *live_out, int64_t *slots_out);
+/* AddVectors (xvec.go:288-318; an UPSERT by id): n vectors go to slots *first_slot_out .. +n-1.
+ * dense: values[n*dim]; sparse: sp_off[n+1] (from 0), sp_indices strictly ascending per vector, values[sp_off[n]].
+ * hidden[n], timestamp_ms[n] (Vector.Timestamp.UnixMilli()), categories as CSR cat_off[n+1] / cats (any may be NULL = none).
+ * replace[n]: the slot currently holding the same id (it is tombstoned), or -1; NULL = all new. */
+int32_t gorse_b200_vecdb_add(gorse_b200_vecdb *db, int64_t n, const float *values, const int64_t *sp_off, const uint32_t *sp_indices,
+                             const uint8_t *hidden, const int64_t *timestamp_ms, const int64_t *cat_off, const int32_t *cats,
+                             const int64_t *replace, int64_t *first_slot_out);
+/* GetVectors (xvec.go:320-363) by slot; live_out[i] = 0 for unknown or deleted slots.  Dense values_out[n*dim]. */
+int32_t gorse_b200_vecdb_get(gorse_b200_vecdb *db, const int64_t *slots, int64_t n, float *values_out, uint8_t *hidden_out,
+                             int64_t *timestamp_out, uint8_t *live_out);
+int32_t gorse_b200_vecdb_get_sparse(gorse_b200_vecdb *db, int64_t slot, uint32_t *indices_out, float *values_out, int32_t cap,
+                                    int32_t *nnz_out);
+/* DeleteVectors(timestamp) (xvec.go:365-371): tombstones live vectors with timestamp < timestamp_ms; the first `cap` deleted
+ * slots are written to slots_out (the shim drops their ids), *count_out = how many were deleted */
+int32_t gorse_b200_vecdb_delete_before(gorse_b200_vecdb *db, int64_t timestamp_ms, int64_t *slots_out, int64_t cap, int64_t *count_out);
+/* QueryVectors (xvec.go:373-449) for nq query vectors sharing one category filter: candidates are live, not hidden and
+ * carry ALL of categories[n_categories] (CONTAIN_ALL, :381-389).  Results per query: slots_out / scores_out [nq x topk],
+ * best first, count_out[nq]; score = dot (Dot) or the NEGATED distance (Euclidean, Cosine) -- higher is more similar
+ * (database.go:101, xvec.go:425-427).  Sparse: only positive dots are returned (the reference drops score 0, :421-423, and
+ * its callers drop score <= 0, logics/item_to_item.go:73); topk <= 128.  topk <= 0 -> no results (:374-376). */
+int32_t gorse_b200_vecdb_query(gorse_b200_vecdb *db, int64_t nq, const float *q_values, const int64_t *q_sp_off, const uint32_t *q_sp_indices,
+                               const int32_t *categories, int32_t n_categories, int32_t topk, int64_t *slots_out, float *scores_out,
+                               int32_t *count_out);
 
 #ifdef __cplusplus
 }

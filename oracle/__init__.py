@@ -237,6 +237,14 @@ def sparse_vector(ids, idf, offset=0):
     return ind[:m], val[:m]
 
 
+def sparse_dot(ia, va, ib, vb):
+    """merge-join dot of two sparse vectors in ascending index order (what the flat sparse index of the reference's vector
+    store computes; restated, see gorse_oracle.h)"""
+    ia, ib = np.ascontiguousarray(ia, np.uint32), np.ascontiguousarray(ib, np.uint32)
+    va, vb = f32(va), f32(vb)
+    return np.float32(lib().gbo_sparse_dot(ia, va, len(ia), ib, vb, len(ib)))
+
+
 def sparse_bruteforce_search(off, indices, values, self_index, k):
     """k best neighbours (ids, dots) of stored sparse vector `self_index` among the CSR-packed vectors."""
     off = i64(off)
