@@ -15,6 +15,8 @@
 //     per-f column walk conflict-free), the running predictions live in registers.
 // In all forms sums over the row's feedback are taken lane-parallel, so results differ from the reference's serial
 // order by reassociation only (parity budget 1e-4 relative, observed ~1e-6).
+#include <cstdlib>
+
 #include "als.cuh"
 
 namespace gb {
@@ -718,8 +720,13 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
                 case 4: ck = als_chunk_gram_kernel<4, false>; break;
                 default: ck = als_chunk_gram_kernel<8, false>; break;
             }
-            ck<<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p);
-            GB_LAUNCHED(c);
+            static const bool no_tc = [] { const char *e = getenv("GORSE_B200_ALS_NO_TC"); return e && atoi(e) == 1; }();   // A/B runs
+            if (d == 128 && !no_tc) {
+                GB_TRY(als_chunk_gram_tc(c, Y, idx, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, nc, cf->als_partial.p));
+            } else {
+                ck<<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p);
+                GB_LAUNCHED(c);
+            }
             const size_t ssm = sizeof(float) * ((size_t)d * (d + 1) + 2 * d);
             als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, rows, cf->als_row_chunk0[side].p, cf->als_partial.p);
             GB_LAUNCHED(c);

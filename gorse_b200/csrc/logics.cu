@@ -102,4 +102,51 @@ int32_t gorse_b200_index_query_similar(gorse_b200_index *ix, int64_t q0, int64_t
     return GORSE_B200_OK;
 }
 
+// ---- model hand-off: cf.BaseMatrixFactorization.Marshal's factor block from the flat mirror ----------------
+// model/cf/model.go:212-245 writes, for users and then items,  int64 LE count of predictable rows  followed by one
+// pbutil.WriteDelimited(protocol.LatentFactor{Id, Data}) per predictable row (protocol/encoding.proto:27-30:
+// string id = 1; repeated float data = 2 -> packed): a varint message length, then  0x0A len id-bytes  (omitted for an empty
+// id, proto3)  and  0x12 varint(4 d) d little-endian floats  (omitted for d = 0).  The reference builds one protobuf object
+// and one slice header per row; this writes the same bytes in one pass over the flat [rows x d] table.
+static size_t put_varint(uint8_t *out, uint64_t v)
+{
+    size_t n = 0;
+    while (v >= 0x80) { if (out) out[n] = (uint8_t)(v | 0x80); n++; v >>= 7; }
+    if (out) out[n] = (uint8_t)v;
+    return n + 1;
+}
+static size_t varint_len(uint64_t v) { return put_varint(nullptr, v); }
+
+int32_t gorse_b200_marshal_latent_factors(const float *factors, int32_t rows, int32_t d, const uint8_t *predictable, const char *const *ids,
+                                          uint8_t *out, size_t cap, size_t *len_out)
+{
+    GB_CHECK_ARG(len_out != nullptr, "len_out is NULL");
+    GB_CHECK_ARG(rows >= 0 && d >= 0, "negative size");
+    GB_CHECK_ARG(rows == 0 || (factors != nullptr && ids != nullptr), "NULL factors/ids");
+    // pass 1: size;  pass 2 (only when the buffer is large enough): bytes
+    int64_t count = 0;
+    size_t need = 8;
+    for (int32_t r = 0; r < rows; r++) {
+        if (predictable && !predictable[r]) continue;
+        GB_CHECK_ARG(ids[r] != nullptr, "ids[%d] is NULL", r);
+        const size_t idl = strlen(ids[r]);
+        const size_t body = (idl ? 1 + varint_len(idl) + idl : 0) + (d ? 1 + varint_len(4ull * d) + 4ull * d : 0);
+        need += varint_len(body) + body;
+        count++;
+    }
+    *len_out = need;
+    if (out == nullptr || cap < need) return out == nullptr ? GORSE_B200_OK : GORSE_B200_ERR_RANGE;
+    uint8_t *p = out;
+    for (int b = 0; b < 8; b++) *p++ = (uint8_t)((uint64_t)count >> (8 * b));   // binary.Write(w, LittleEndian, int64(count))
+    for (int32_t r = 0; r < rows; r++) {
+        if (predictable && !predictable[r]) continue;
+        const size_t idl = strlen(ids[r]);
+        const size_t body = (idl ? 1 + varint_len(idl) + idl : 0) + (d ? 1 + varint_len(4ull * d) + 4ull * d : 0);
+        p += put_varint(p, body);
+        if (idl) { *p++ = 0x0A; p += put_varint(p, idl); memcpy(p, ids[r], idl); p += idl; }
+        if (d) { *p++ = 0x12; p += put_varint(p, 4ull * d); memcpy(p, factors + (int64_t)r * d, 4ull * d); p += 4ull * d; }   // x86 / arm64 are little-endian
+    }
+    return GORSE_B200_OK;
+}
+
 }  // extern "C"

@@ -332,6 +332,22 @@ static int32_t search_common(gorse_b200_index *ix, const float *h_queries, const
     return done(GORSE_B200_OK);
 }
 
+// make room for `need` vectors (amortised doubling); the caller holds ix->mu
+int32_t index_reserve(gorse_b200_index *ix, int64_t need)
+{
+    if (need <= ix->cap) return GORSE_B200_OK;
+    cudaStream_t s = ix->ctx->stream;
+    const int64_t ncap = std::max<int64_t>(need, ix->cap * 2);
+    DevBuf<float> nb;
+    GB_TRY(nb.alloc((size_t)ncap * ix->d));
+    if (ix->n) GB_CUDA(cudaMemcpyAsync(nb.p, ix->X.p, sizeof(float) * ix->n * ix->d, cudaMemcpyDeviceToDevice, s));
+    GB_CUDA(cudaStreamSynchronize(s));
+    ix->X.free();
+    ix->X = nb;
+    ix->cap = ncap;
+    return GORSE_B200_OK;
+}
+
 }  // namespace gb
 
 using namespace gb;
@@ -380,16 +396,7 @@ int32_t gorse_b200_index_add(gorse_b200_index *ix, const float *vectors, int64_t
         ScopedDevice sd(ix->ctx->device);
         cudaStream_t s = ix->ctx->stream;
         int64_t need = ix->n + n;
-        if (need > ix->cap) {
-            int64_t ncap = std::max<int64_t>(need, ix->cap * 2);
-            DevBuf<float> nb;
-            GB_TRY(nb.alloc((size_t)ncap * ix->d));
-            if (ix->n) GB_CUDA(cudaMemcpyAsync(nb.p, ix->X.p, sizeof(float) * ix->n * ix->d, cudaMemcpyDeviceToDevice, s));
-            GB_CUDA(cudaStreamSynchronize(s));
-            ix->X.free();
-            ix->X = nb;
-            ix->cap = ncap;
-        }
+        GB_TRY(index_reserve(ix, need));
         GB_CUDA(cudaMemcpyAsync(ix->X.p + ix->n * ix->d, vectors, sizeof(float) * n * ix->d, cudaMemcpyHostToDevice, s));
         GB_CUDA(cudaStreamSynchronize(s));
         ix->n = need;

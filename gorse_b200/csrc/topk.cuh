@@ -38,6 +38,7 @@ int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t
                            const int32_t *row_list, int32_t *d_idx, float *d_dist, int32_t *d_count, int prune0, int *d_nan,
                            const uint8_t *allow = nullptr);
 
+int32_t index_reserve(gorse_b200_index *ix, int64_t need);
 bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k);
 int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,
                    int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan);

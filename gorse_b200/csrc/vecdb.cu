@@ -16,6 +16,7 @@
 // string <-> int32 map, the library works on slots (int64, in insertion order) and category ids.
 #include <algorithm>
 
+#include "cf.cuh"
 #include "sparse.cuh"
 #include "topk.cuh"
 
@@ -57,6 +58,24 @@ __global__ void vecdb_allow_kernel(const uint8_t *blocked, const int64_t *cat_of
         ok = has;
     }
     allow[i] = ok ? 1 : 0;
+}
+
+// flag[item] = 1 for every item with >= 1 training feedback (IsItemPredictable, model/cf/model.go:129-146)
+__global__ void vecdb_mark_items_kernel(const int32_t *user_items, int64_t n, int32_t *flag)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += st) flag[user_items[i]] = 1;
+}
+// X[first + s] = Q[items[s]]  (device to device, float4 per thread)
+__global__ void vecdb_copy_rows_kernel(const float *Q, int d4, const int32_t *items, int64_t n, float *X)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = n * d4, st = (int64_t)gridDim.x * blockDim.x;
+    for (; i < total; i += st) {
+        const int64_t s = i / d4, c = i - s * d4;
+        reinterpret_cast<float4 *>(X)[s * d4 + c] = reinterpret_cast<const float4 *>(Q)[(int64_t)items[s] * d4 + c];
+    }
 }
 
 static int32_t sync_meta(gorse_b200_vecdb *db)
@@ -294,6 +313,76 @@ int32_t gorse_b200_vecdb_query(gorse_b200_vecdb *db, int64_t nq, const float *q_
     if (st) return st;
     for (int64_t t = 0; t < nq * topk; t++) slots_out[t] = idx[(size_t)t];
     return GORSE_B200_OK;
+}
+
+// master/tasks.go:925-961: after Fit the item factors of the predictable items become the "collaborative_filtering_<id>"
+// collection (distance Dot).  The reference walks GetItemFactor(i) row by row into []vectors.Vector batches; here the rows go
+// from the model's item table to the collection device to device.  slot_of_item_out[n_items]: the slot of each item, -1 for
+// items without training feedback (they are skipped, :943).  Single-GPU models (the replicated Q of a distributed model is
+// complete on every rank, but predictability needs all ranks' rows).
+int32_t gorse_b200_vecdb_add_item_factors(gorse_b200_vecdb *db, gorse_b200_cf *cf, const uint8_t *hidden, int64_t timestamp_ms,
+                                          const int64_t *cat_off, const int32_t *cats, int64_t *slot_of_item_out)
+{
+    GB_CHECK_ARG(db != nullptr && cf != nullptr, "NULL collection / model");
+    GB_CHECK_ARG(db->dim == cf->d, "collection dimension %d != model factors %d", db->dim, cf->d);
+    GB_CHECK_ARG(cf->ctx->world == 1, "hand-off from a distributed model is not supported");
+    GB_CHECK_ARG(db->ctx->device == cf->ctx->device, "collection and model live on different devices");
+    GB_CHECK_ARG(cat_off == nullptr || cat_off[0] == 0, "cat_off[0] must be 0");
+    std::lock_guard<std::mutex> lk(db->mu);
+    gorse_b200_ctx *c = db->ctx;
+    ScopedDevice sd(c->device);
+    const int32_t I = cf->n_items;
+    DevBuf<int32_t> d_flag, d_items;
+    auto done = [&](int32_t s) { cudaStreamSynchronize(c->stream); d_flag.free(); d_items.free(); return s; };
+    int32_t st;
+    if ((st = d_flag.alloc((size_t)std::max(I, 1)))) return done(st);
+    cudaError_t e = cudaMemsetAsync(d_flag.p, 0, sizeof(int32_t) * (size_t)std::max(I, 1), c->stream);
+    if (e == cudaSuccess && cf->n_feedback > 0) {
+        vecdb_mark_items_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(cf->user_items.p, cf->n_feedback, d_flag.p);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    std::vector<int32_t> flag((size_t)I);
+    if (e == cudaSuccess && I) e = cudaMemcpyAsync(flag.data(), d_flag.p, sizeof(int32_t) * (size_t)I, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { set_error("add_item_factors: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+    std::vector<int32_t> items;
+    const int64_t first = (int64_t)db->ts.size();
+    for (int32_t i = 0; i < I; i++) {
+        if (slot_of_item_out) slot_of_item_out[i] = flag[(size_t)i] ? first + (int64_t)items.size() : -1;
+        if (flag[(size_t)i]) items.push_back(i);
+    }
+    const int64_t n = (int64_t)items.size();
+    if (n == 0) return done(GORSE_B200_OK);
+    gorse_b200_index *ix = db->dense;
+    {
+        std::lock_guard<std::mutex> lk2(ix->mu);
+        if ((st = index_reserve(ix, ix->n + n))) return done(st);
+        if ((st = d_items.alloc((size_t)n))) return done(st);
+        e = cudaMemcpyAsync(d_items.p, items.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            if (cf->d % 4 == 0) vecdb_copy_rows_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(cf->Q.p, cf->d / 4, d_items.p, n, ix->X.p + ix->n * ix->d);
+            else for (int64_t s2 = 0; s2 < n && e == cudaSuccess; s2++)
+                e = cudaMemcpyAsync(ix->X.p + (ix->n + s2) * ix->d, cf->Q.p + (int64_t)items[(size_t)s2] * cf->d, sizeof(float) * cf->d, cudaMemcpyDeviceToDevice, c->stream);
+            c->launches++;
+            if (e == cudaSuccess) e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { set_error("add_item_factors: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
+        ix->n += n;
+        ix->mma_ready = false;
+    }
+    for (int64_t s2 = 0; s2 < n; s2++) {
+        const int32_t it = items[(size_t)s2];
+        db->hidden.push_back(hidden ? (hidden[it] != 0) : 0);
+        db->dead.push_back(0);
+        db->ts.push_back(timestamp_ms);
+        if (cat_off) db->cats.insert(db->cats.end(), cats + cat_off[it], cats + cat_off[it + 1]);
+        db->cat_off.push_back((int64_t)db->cats.size());
+        db->live++;
+    }
+    db->meta_dirty = true;
+    return done(GORSE_B200_OK);
 }
 
 }  // extern "C"

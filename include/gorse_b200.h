@@ -285,6 +285,13 @@ int32_t gorse_b200_similar_scores(int32_t metric, double score_scale, int32_t se
  * count_out[q1-q0] */
 int32_t gorse_b200_index_query_similar(gorse_b200_index *ix, int64_t q0, int64_t q1, int32_t n, double score_scale,
                                        int32_t *ids_out, double *scores_out, int32_t *count_out);
+/* Model hand-off: the factor block of cf.BaseMatrixFactorization.Marshal (model/cf/model.go:212-245) for one
+ * table straight from the flat host mirror: int64 LE count of predictable rows, then one varint-delimited
+ * protocol.LatentFactor{id = 1, data = 2 packed} per predictable row (protocol/encoding.proto:27-30), byte for byte what
+ * pbutil.WriteDelimited emits.  predictable == NULL: every row.  Host function.  *len_out = bytes needed; with out == NULL
+ * only the size is computed; a too small buffer gives GORSE_B200_ERR_RANGE. */
+int32_t gorse_b200_marshal_latent_factors(const float *factors, int32_t rows, int32_t d, const uint8_t *predictable, const char *const *ids,
+                                          uint8_t *out, size_t cap, size_t *len_out);
 
 /* ------------------------------------------------------------------------------------------
  * Sparse index: brute-force search over sparse
@@ -342,6 +349,11 @@ int32_t gorse_b200_vecdb_delete_before(gorse_b200_vecdb *db, int64_t timestamp_m
  * best first, count_out[nq]; score = dot (Dot) or the NEGATED distance (Euclidean, Cosine) -- higher is more similar
  * (database.go:101, xvec.go:425-427).  Sparse: only positive dots are returned (the reference drops score 0, :421-423, and
  * its callers drop score <= 0, logics/item_to_item.go:73); topk <= 128.  topk <= 0 -> no results (:374-376). */
+/* Model hand-off (master/tasks.go:925-961): the item factors of every item with >= 1 training feedback (IsItemPredictable)
+ * become vectors of a Dot collection, device to device -- no GetItemFactor round trip.  hidden[n_items], categories CSR over
+ * items (may be NULL), one timestamp (the model id, :925).  slot_of_item_out[n_items]: slot per item, -1 = not predictable. */
+int32_t gorse_b200_vecdb_add_item_factors(gorse_b200_vecdb *db, gorse_b200_cf *cf, const uint8_t *hidden, int64_t timestamp_ms,
+                                          const int64_t *cat_off, const int32_t *cats, int64_t *slot_of_item_out);
 int32_t gorse_b200_vecdb_query(gorse_b200_vecdb *db, int64_t nq, const float *q_values, const int64_t *q_sp_off, const uint32_t *q_sp_indices,
                                const int32_t *categories, int32_t n_categories, int32_t topk, int64_t *slots_out, float *scores_out,
                                int32_t *count_out);

@@ -83,3 +83,54 @@ def test_oracle_sparse_search_reference_known_answers(orc):
         s_ids, s_sc = orc.similar_scores(False, 0.5, q, 10, ids, dots)
         assert s_ids.tolist() == want
         assert s_sc.tolist() == [0.5 * (100 - j) for j in want]
+
+
+def test_marshal_latent_factors_is_the_reference_wire_format(gb):
+    """gorse_b200_marshal_latent_factors == the factor block of cf.BaseMatrixFactorization.Marshal (model/cf/model.go:212-245):
+    int64 LE count + varint-delimited protocol.LatentFactor{id = 1, data = 2 packed} (protocol/encoding.proto:27-30).
+    Checked against hand-assembled protobuf bytes and by decoding with an independent varint parser."""
+    import ctypes as C
+
+    from gorse_b200 import _lib
+
+    F = np.arange(12, dtype=np.float32).reshape(4, 3) * 0.5 - 1
+    ids = [b"u0", b"", b"user-with-a-much-longer-identifier-" + b"x" * 120, b"u3"]
+    pred = np.array([1, 1, 1, 0], np.uint8)
+    arr = (C.c_char_p * 4)(*ids)
+    n = C.c_size_t(0)
+    assert _lib.lib.gorse_b200_marshal_latent_factors(gb.ptr(F), 4, 3, gb.ptr(pred), arr, None, 0, C.byref(n)) == 0
+    buf = np.zeros(n.value, np.uint8)
+    assert _lib.lib.gorse_b200_marshal_latent_factors(gb.ptr(F), 4, 3, gb.ptr(pred), arr, gb.ptr(buf), buf.size, C.byref(n)) == 0
+    assert _lib.lib.gorse_b200_marshal_latent_factors(gb.ptr(F), 4, 3, gb.ptr(pred), arr, gb.ptr(buf), buf.size - 1, C.byref(n)) == _lib.ERR_RANGE
+    raw = buf.tobytes()
+
+    def varint(b, p):
+        v = s = 0
+        while True:
+            v |= (b[p] & 0x7F) << s
+            p += 1
+            if b[p - 1] < 0x80:
+                return v, p
+            s += 7
+
+    assert int.from_bytes(raw[:8], "little") == 3
+    p, rows = 8, []
+    while p < len(raw):
+        ln, p = varint(raw, p)
+        msg, p = raw[p:p + ln], p + ln
+        q, rid, data = 0, b"", None
+        while q < len(msg):
+            tag, q = varint(msg, q)
+            ln2, q = varint(msg, q)
+            if tag == 0x0A:
+                rid = msg[q:q + ln2]
+            else:
+                assert tag == 0x12
+                data = np.frombuffer(msg[q:q + ln2], "<f4")
+            q += ln2
+        rows.append((rid, data))
+    assert [r[0] for r in rows] == ids[:3] and all(np.array_equal(rows[i][1], F[i]) for i in range(3))
+    # first message by hand: len 18 = (0x0A 2 'u0') + (0x12 12 <3 floats>)
+    assert raw[8:12] == bytes([18, 0x0A, 2]) + b"u"[:1] and raw[12:14] == b"0" + bytes([0x12]) and raw[14] == 12
+    # empty id: the field is omitted (proto3 default); long id: two-byte varint lengths
+    assert raw[8 + 19] == 14 and raw[8 + 20] == 0x12

@@ -153,3 +153,35 @@ def test_sparse_filtered_queries_match_the_oracle(gb, orc, ctx):
                 order = sorted([j for j in range(N) if dots[j] > 0], key=lambda j: (-dots[j], j))[:k]
                 assert cnt[qi] == len(order) and slots[qi, :cnt[qi]].tolist() == order
                 assert scores[qi, :cnt[qi]].tobytes() == dots[order].tobytes()
+
+
+def test_item_factors_hand_off(gb, orc, ctx):
+    """master/tasks.go:925-961 without the host round trip: the predictable items' factor rows go device to device into a Dot
+    collection; CF retrieval then == the oracle's brute force over those rows (worker/worker_test.go:194-221 pattern)."""
+    import ctypes as C
+
+    from gorse_b200 import _lib, synth
+
+    U, I, d = 300, 120, 32
+    # feedback only touches items 0..99: items 100..119 are not predictable
+    o2, it2 = synth.make_feedback(U, 100, 2500, seed=3)
+    rng = np.random.default_rng(0)
+    P = rng.standard_normal((U, d)).astype(np.float32)
+    Q = rng.standard_normal((I, d)).astype(np.float32)
+    hidden = (rng.random(I) < 0.1).astype(np.uint8)
+    with gb.CFModel(ctx, U, I, d, o2, it2) as m, gb.VectorCollection(ctx, d, gb.DISTANCE_DOT) as col:
+        m.set_factors(P, Q)
+        slot = np.zeros(I, np.int64)
+        gb.check(_lib.lib.gorse_b200_vecdb_add_item_factors(col.h, m.h, gb.ptr(hidden), 1234, None, None, gb.ptr(slot)))
+        present = np.zeros(I, bool)
+        present[np.unique(it2)] = True
+        assert ((slot >= 0) == present).all() and slot[present].tolist() == list(range(present.sum()))
+        assert col.count() == (int(present.sum()), int(present.sum()))
+        vals, hid, ts, live = col.get(slot[present][:5])
+        assert vals.tobytes() == Q[np.nonzero(present)[0][:5]].tobytes() and (ts == 1234).all()
+        s, sc, n = col.query(P[:20], [], 10)
+        ids = np.nonzero(present & (hidden == 0))[0]
+        for u in range(20):
+            oi, od = orc.bruteforce_search(np.ascontiguousarray(Q[ids]), P[u], 10, metric=orc.METRIC_NEG_DOT)
+            assert sc[u, :n[u]].tobytes() == (-od).astype(np.float32).tobytes()
+            assert [int(np.nonzero(slot == x)[0][0]) for x in s[u, :n[u]]] == ids[oi].tolist() or len(set(od.tolist())) < len(od)
