@@ -85,6 +85,8 @@ struct gorse_b200_ctx {
     int sm_count = 148;
     int rank = 0, world = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // result downloads that overlap the next chunk's kernels (topk)
+    cudaEvent_t copy_ev = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     ncclComm_t comm = nullptr;
     int64_t launches = 0;

@@ -99,6 +99,8 @@ static int32_t ctx_create_common(int32_t device, gorse_b200_ctx **out)
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     GB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    GB_CUDA(cudaEventCreateWithFlags(&c->copy_ev, cudaEventDisableTiming));
     GB_CUDA(cudaEventCreate(&c->ev0));
     GB_CUDA(cudaEventCreate(&c->ev1));
     *out = c;
@@ -150,6 +152,8 @@ int32_t gorse_b200_ctx_destroy(gorse_b200_ctx *ctx)
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->copy_ev) cudaEventDestroy(ctx->copy_ev);
     delete ctx;
     return GORSE_B200_OK;
 }

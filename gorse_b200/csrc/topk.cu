@@ -291,17 +291,20 @@ static int32_t search_common(gorse_b200_index *ix, const float *h_queries, const
     GB_CHECK_ARG(idx_out != nullptr && dist_out != nullptr, "NULL output");
     ScopedDevice sd(ix->ctx->device);
     gorse_b200_ctx *c = ix->ctx;
-    DevBuf<float> d_q, d_dist;
+    DevBuf<float> d_q;
     DevBuf<int64_t> d_qidx;
-    DevBuf<int32_t> d_idx, d_count;
     DevBuf<int> d_nan;
+    DevBuf<int32_t> &d_idx = ix->r_idx, &d_count = ix->r_count;   // grow-only staging kept in the index
+    DevBuf<float> &d_dist = ix->r_dist;
     int32_t st = GORSE_B200_OK;
     auto done = [&](int32_t s) {
         cudaStreamSynchronize(c->stream);
-        d_q.free(); d_dist.free(); d_qidx.free(); d_idx.free(); d_count.free(); d_nan.free();
+        cudaStreamSynchronize(c->copy_stream);
+        d_q.free(); d_qidx.free(); d_nan.free();
         return s;
     };
-    if ((st = d_idx.alloc((size_t)nq * k)) || (st = d_dist.alloc((size_t)nq * k)) || (st = d_count.alloc(nq)) || (st = d_nan.alloc(1)))
+    if ((d_idx.n < (size_t)nq * k && (st = d_idx.alloc((size_t)nq * k))) || (d_dist.n < (size_t)nq * k && (st = d_dist.alloc((size_t)nq * k))) ||
+        (d_count.n < (size_t)nq && (st = d_count.alloc(nq))) || (st = d_nan.alloc(1)))
         return done(st);
     cudaError_t e = cudaMemsetAsync(d_nan.p, 0, sizeof(int), c->stream);
     if (h_queries) {
@@ -313,18 +316,20 @@ static int32_t search_common(gorse_b200_index *ix, const float *h_queries, const
     }
     if (e != cudaSuccess) { set_error("search upload: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
     // large all-pairs / batched problems go through the tensor-core candidate generator + exact re-rank
+    bool downloaded = false;
     if (mma_path_eligible(ix, nq, k)) {
-        st = search_mma(ix, d_q.p, d_qidx.p, q0, nq, k, prune0, d_idx.p, d_dist.p, d_count.p, d_nan.p);
+        st = search_mma(ix, d_q.p, d_qidx.p, q0, nq, k, prune0, d_idx.p, d_dist.p, d_count.p, d_nan.p, idx_out, dist_out, count_out);
+        downloaded = true;
     } else {
         st = launch_exact(ix, d_q.p, d_qidx.p, q0, nq, k, nullptr, nullptr, 0, nullptr, d_idx.p, d_dist.p, d_count.p, prune0, d_nan.p);
     }
     if (st) return done(st);
     int h_nan = 0;
-    if ((e = cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * nq * k, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(dist_out, d_dist.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaMemcpyAsync(count_out, d_count.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+    if ((!downloaded && ((e = cudaMemcpyAsync(idx_out, d_idx.p, sizeof(int32_t) * nq * k, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+                         (e = cudaMemcpyAsync(dist_out, d_dist.p, sizeof(float) * nq * k, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
+                         (e = cudaMemcpyAsync(count_out, d_count.p, sizeof(int32_t) * nq, cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess)) ||
         (e = cudaMemcpyAsync(&h_nan, d_nan.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess ||
-        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess) {
+        (e = cudaStreamSynchronize(c->stream)) != cudaSuccess || (e = cudaStreamSynchronize(c->copy_stream)) != cudaSuccess) {
         set_error("search: %s", cudaGetErrorString(e));
         return done(GORSE_B200_ERR_CUDA);
     }
@@ -382,6 +387,7 @@ int32_t gorse_b200_index_destroy(gorse_b200_index *ix)
     if (ix->ev0) { cudaEventDestroy(ix->ev0); cudaEventDestroy(ix->ev1); }
     ix->w_qb.free(); ix->w_eps.free(); ix->w_cval.free(); ix->w_theta.free();
     ix->w_ccol.free(); ix->w_ccnt.free(); ix->w_ids.free(); ix->w_idcnt.free(); ix->w_flag.free(); ix->w_flist.free();
+    ix->r_idx.free(); ix->r_count.free(); ix->r_dist.free();
     delete ix;
     return GORSE_B200_OK;
 }

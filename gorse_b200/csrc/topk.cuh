@@ -24,6 +24,9 @@ struct gorse_b200_index {
     gb::DevBuf<__nv_bfloat16> w_qb;
     gb::DevBuf<float> w_eps, w_cval, w_theta;
     gb::DevBuf<int32_t> w_ccol, w_ccnt, w_ids, w_idcnt, w_flag, w_flist;
+    // result staging of search_common (grow-only: a 120 MB cudaMalloc + cudaFree per all-pairs call otherwise)
+    gb::DevBuf<int32_t> r_idx, r_count;
+    gb::DevBuf<float> r_dist;
     std::mutex mu;
 };
 
@@ -40,7 +43,10 @@ int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t
 
 int32_t index_reserve(gorse_b200_index *ix, int64_t need);
 bool mma_path_eligible(const gorse_b200_index *ix, int64_t nq, int k);
+// h_*: optional host result buffers; when given, every finished chunk of queries is downloaded on the context's copy stream
+// while the next chunk's kernels run
 int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,
-                   int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan);
+                   int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan, int32_t *h_idx = nullptr, float *h_dist = nullptr,
+                   int32_t *h_count = nullptr);
 
 }  // namespace gb

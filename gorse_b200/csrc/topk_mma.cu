@@ -455,7 +455,7 @@ static int32_t ensure_mirror(gorse_b200_index *ix)
 }
 
 int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx, int64_t q0, int64_t nq, int k, int prune0,
-                   int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan)
+                   int32_t *d_idx, float *d_dist, int32_t *d_count, int *d_nan, int32_t *h_idx, float *h_dist, int32_t *h_count)
 {
     gorse_b200_ctx *c = ix->ctx;
     GB_TRY(ensure_mirror(ix));
@@ -463,8 +463,10 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     const int64_t n_pad = (ix->n + mma::BN - 1) / mma::BN * mma::BN;
     const int n_tiles = (int)(n_pad / mma::BN);
     // sample size: the R_TOP-th best of m random columns leaves on average R_TOP * N / m columns above it (Gamma(R_TOP)
-    // spread).  Aim for 3.2k: fewer than k with probability ~2e-4, and far below the CAP-slot candidate list.
-    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (3.2 * k) / mma::BN);
+    // spread).  Aim for 4.5k: fewer than k with probability ~6e-6 (3.2k, the round-1 value, failed for ~2e-4 of the rows = 30
+    // rows of a 151 552-row call, and each failed row costs a full exact scan: 9 ms per call against +3 ms of prune / re-rank
+    // work for the longer candidate lists), still far below the CAP-slot candidate list.
+    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (4.5 * k) / mma::BN);
     m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
@@ -475,8 +477,9 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
 
     CUtensorMap map_b;
     GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
-    // queries are processed in chunks so that the candidate lists stay modest
-    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM * 4;
+    // queries are processed in chunks of one 256-row group per SM: the candidate lists stay modest and the download of a
+    // finished chunk's results (copy stream) overlaps the next chunk's kernels
+    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM;
     // work buffers live in the index and are reused by later searches (multi-GB cudaMalloc/cudaFree per call otherwise)
     DevBuf<__nv_bfloat16> &Qb = ix->w_qb;
     DevBuf<float> &eps = ix->w_eps, &cval = ix->w_cval, &theta = ix->w_theta;
@@ -484,6 +487,7 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     int32_t st = GORSE_B200_OK;
     auto done = [&](int32_t s) {
         cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->copy_stream);
         return s;
     };
     const int64_t cq = std::min(nq, chunk), cq_pad = (cq + 255) / 256 * 256;
@@ -551,6 +555,16 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         if (n_fb > 0) {
             if ((st = launch_exact_split(ix, qp, qi, q0 + off, n_fb, k, flist.p, d_idx + off * k, d_dist + off * k, d_count + off, prune0, d_nan)))
                 return done(st);
+        }
+        if (h_idx) {
+            // this chunk is final: download it on the copy stream while the next chunk computes
+            if ((e = cudaEventRecord(c->copy_ev, c->stream)) != cudaSuccess || (e = cudaStreamWaitEvent(c->copy_stream, c->copy_ev, 0)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(h_idx + off * k, d_idx + off * k, sizeof(int32_t) * n_this * k, cudaMemcpyDeviceToHost, c->copy_stream)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(h_dist + off * k, d_dist + off * k, sizeof(float) * n_this * k, cudaMemcpyDeviceToHost, c->copy_stream)) != cudaSuccess ||
+                (e = cudaMemcpyAsync(h_count + off, d_count + off, sizeof(int32_t) * n_this, cudaMemcpyDeviceToHost, c->copy_stream)) != cudaSuccess) {
+                set_error("search_mma download: %s", cudaGetErrorString(e));
+                return done(GORSE_B200_ERR_CUDA);
+            }
         }
     }
     if ((e = cudaGetLastError()) != cudaSuccess) { set_error("search_mma: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
