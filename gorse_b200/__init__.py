@@ -456,6 +456,23 @@ class VectorCollection:
         self.close()
 
 
+def load_ncf(train_path, test_path=None):
+    """dataset.LoadDataFromBuiltIn's NCF parsers (dataset/dataset.go:398-490) ->
+    (n_users, n_items, (train_off, train_items), (test_off, test_items), (neg_off, neg_items))."""
+    h = C.c_void_p()
+    check(lib.gorse_b200_ncf_load(str(train_path).encode(), str(test_path).encode() if test_path else None, C.byref(h)))
+    try:
+        U, I = C.c_int32(0), C.c_int32(0)
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(lib.gorse_b200_ncf_shape(h, C.byref(U), C.byref(I), C.byref(a), C.byref(b), C.byref(c)))
+        offs = [np.zeros(U.value + 1, np.int64) for _ in range(3)]
+        idx = [np.zeros(n.value, np.int32) for n in (a, b, c)]
+        check(lib.gorse_b200_ncf_get(h, ptr(offs[0]), ptr(idx[0]), ptr(offs[1]), ptr(idx[1]), ptr(offs[2]), ptr(idx[2])))
+    finally:
+        lib.gorse_b200_ncf_free(h)
+    return U.value, I.value, (offs[0], idx[0]), (offs[1], idx[1]), (offs[2], idx[2])
+
+
 # ---- logics: similarity vectors and scores (host functions; SURVEY 8a row J) ---------------------------------
 def bf16_truncate(a):
     """bfloats.FromFloat32 + ToFloat32 (common/bfloats/bfloats.go:23-37): how the reference stores dense embeddings."""

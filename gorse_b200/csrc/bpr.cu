@@ -105,9 +105,8 @@ __device__ __forceinline__ void bpr_step_rows(const Rows<C> &r, float *Pu, float
     }
 }
 
-// same step, atomic flavour, but the positive (hot) row's DATA delta lr*g*p is returned in dq instead of being issued: the
-// caller sums it over the 8 quads of its warp (all on the same hot row) and issues one red.  The row's regularisation
-// -lr*reg*q_i is NOT part of dq: the slot's leader warp applies it for everybody (bpr_hot_apply_kernel).
+// same step, atomic flavour, but the positive (hot) row's delta lr*(g*p - reg*q_i) is returned in dq instead of
+// being issued: the caller sums it over the 8 quads of its warp (all on the same hot row) and issues one red
 template <int C>
 __device__ __forceinline__ void bpr_step_rows_hot(const Rows<C> &r, bool live, float *Pu, float *Qj, int sj, unsigned mask,
                                                   float lr, float reg, float4 (&dq)[C])
@@ -127,7 +126,8 @@ __device__ __forceinline__ void bpr_step_rows_hot(const Rows<C> &r, bool live, f
 #pragma unroll
     for (int c = 0; c < C; c++) {
         float4 t, o;
-        GB_F4_OP(dq[c], __fmul_rn(__fmul_rn(g, f4get(p[c], k_)), lr));
+        GB_F4_OP(t, __fmaf_rn(f4get(qi[c], k_), nreg, __fmul_rn(g, f4get(p[c], k_))));
+        GB_F4_OP(dq[c], __fmul_rn(f4get(t, k_), lr));
         GB_F4_OP(t, __fmaf_rn(f4get(qj[c], k_), nreg, __fmul_rn(ng, f4get(p[c], k_))));
         GB_F4_OP(o, __fmul_rn(f4get(t, k_), lr)); red_row(Qj + sj * c, o);
         GB_F4_OP(t, __fmaf_rn(f4get(p[c], k_), nreg, __fmul_rn(__fsub_rn(f4get(qi[c], k_), f4get(qj[c], k_)), g)));
@@ -237,16 +237,16 @@ __device__ __forceinline__ float *item_ref(const BprView &v, int32_t it, int32_t
 // per triple on one striped row sustain only ~2*10^8 updates/s).
 // (Prefetching the user row two rounds ahead into L2 was measured in round 2: 3.770 vs 3.772 ms per C2 epoch, no effect;
 // removed.)
-// Regularisation of a hot row (round 2).  Every SGD step shrinks its positive row by lr*reg*q_i.  With k_h steps of the same
-// row in flight, each computed from its own stale copy, the row is shrunk by k_h*lr*reg*q_stale per round: that is what
-// made the factors oscillate and blow up once k_h*lr*reg approached 2 (round 1: stable at <= 1 900 overlapping updates,
-// diverged at 3 800, lr*reg = 5e-4) and why round 1 capped k_h at 768.  Here the shrink is applied by ONE agent on the
-// CURRENT value: every warp counts the steps it applied (pending[slot]); the slot's leader warp collects the count c each
-// round and adds -(1 - (1 - lr*reg)^c) * q_i read this round; hot_scatter_kernel applies what is left at the end.  A
-// multiplicative factor in (0, 1] applied by a single agent cannot overshoot, whatever the concurrency.
+// (Round 2 also tried to lift the concurrency cap: the instability of round 1 is the row's REGULARISATION applied k_h times
+// per round from stale copies -- k_h*lr*reg reached ~2 where it diverged -- so the shrink was moved to one leader warp per slot
+// that applies (1 - lr*reg)^count to the current value.  That is stable at any cap (100 epochs at 3072, Zipf 1.0 and 1.3), but
+// it buys nothing: 4.21 / 3.81 / 3.87 ms per epoch at cap 768 / 1536 / 3072 against 3.87 ms for this kernel at 768, and the
+// fit gets WORSE with the cap (NDCG@10 0.584 / 0.573 / 0.553 at Zipf 1.0; 0.839 / 0.817 / 0.751 at Zipf 1.3): stale gradients
+// on the head of the popularity distribution cost quality long before they cost stability.  The cap is a quality knob, not
+// only a stability knob; profiles/r02_bpr_hot_cap_sweep.md.  Removed.)
 template <int C>
 __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot, const unsigned *begin, const unsigned *first_quad,
-                                                            const int32_t *sorted, float lr, float reg, unsigned *pending)
+                                                            const int32_t *sorted, float lr, float reg)
 {
     const int lane = threadIdx.x & 31, lane4 = lane & 3;
     const unsigned mask = quad_mask();
@@ -260,8 +260,6 @@ __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot
     const int slot = lo;
     const unsigned k = first_quad[slot + 1] - first_quad[slot], r0 = g - first_quad[slot];
     const unsigned b = begin[slot], e = begin[slot + 1];
-    const bool leader = r0 < 8u;                      // the first warp of the slot
-    const float log_keep = log1pf(-lr * reg);         // log(1 - lr*reg)
     const int sh = 4 * v.hot_pad * GB_HOT_SLOT_FLOATS;
     float *Qh = v.hot + ((int64_t)lane4 * v.hot_pad + slot) * GB_HOT_SLOT_FLOATS;
     // three-deep software pipeline per quad: entry t is computed while the cold rows (p_u, q_j) of entry t+k are in
@@ -313,15 +311,6 @@ __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot
         float4 dq[C];
         bpr_step_rows_hot<C>(r, live, Pu, Qj, sj, mask, lr, reg, dq);
         __syncwarp();
-        // steps this warp applied in this round; the leader turns all pending steps of the slot into one shrink
-        const unsigned n_live = (unsigned)__popc(__ballot_sync(0xffffffffu, live && lane4 == 0));
-        float shrink = 0.f;
-        if (leader) {
-            unsigned cnt = 0;
-            if (lane == 0) cnt = atomicExch(pending + slot, 0u) + n_live;
-            cnt = __shfl_sync(0xffffffffu, cnt, 0);
-            shrink = expm1f((float)cnt * log_keep);   // (1 - lr*reg)^cnt - 1  in (-1, 0]
-        } else if (lane == 0 && n_live) atomicAdd(pending + slot, n_live);
 #pragma unroll
         for (int c = 0; c < C; c++) {
 #pragma unroll
@@ -329,15 +318,7 @@ __global__ void __launch_bounds__(256) bpr_hot_apply_kernel(BprView v, int n_hot
                 dq[c].x += __shfl_xor_sync(0xffffffffu, dq[c].x, sft); dq[c].y += __shfl_xor_sync(0xffffffffu, dq[c].y, sft);
                 dq[c].z += __shfl_xor_sync(0xffffffffu, dq[c].z, sft); dq[c].w += __shfl_xor_sync(0xffffffffu, dq[c].w, sft);
             }
-            if (lane < 4) {
-                if (leader) {
-                    // r.qi was read by this lane's quad this round (lanes 0-3 form quad 0); a dead quad re-reads the row
-                    const float4 qc = live ? r.qi[c] : ld_row(Qh + sh * c);
-                    dq[c].x = __fmaf_rn(shrink, qc.x, dq[c].x); dq[c].y = __fmaf_rn(shrink, qc.y, dq[c].y);
-                    dq[c].z = __fmaf_rn(shrink, qc.z, dq[c].z); dq[c].w = __fmaf_rn(shrink, qc.w, dq[c].w);
-                }
-                red_row(Qh + sh * c, dq[c]);
-            }
+            if (lane < 4) red_row(Qh + sh * c, dq[c]);
         }
 #pragma unroll
         for (int c = 0; c < C; c++) { r.p[c] = rn.p[c]; r.qj[c] = rn.qj[c]; }
@@ -527,20 +508,6 @@ __global__ void q_apply_scalar_kernel(float *q, float *q0, int64_t n, int d, con
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, st = (int64_t)gridDim.x * blockDim.x;
     for (; i < n; i += st) { float r = q0[i] + xchg_scale(xchg, n_items, (int32_t)(i / d)) * q[i]; q[i] = r; q0[i] = r; }
-}
-
-// hot rows back to the item table, with the shrink of the steps the leaders had not collected yet
-__global__ void hot_scatter_decay_kernel(float *Q, int d, const int32_t *hot_items, int n_hot, int hot_pad, const float *hot, const unsigned *pending,
-                                         float log_keep)
-{
-    int pieces = d / 4;
-    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (int64_t)n_hot * pieces) return;
-    int s = (int)(t / pieces), pc = (int)(t % pieces);
-    float4 v = *reinterpret_cast<const float4 *>(hot + ((int64_t)pc * hot_pad + s) * GB_HOT_SLOT_FLOATS);
-    const float keep = expf((float)pending[s] * log_keep);
-    v.x *= keep; v.y *= keep; v.z *= keep; v.w *= keep;
-    *reinterpret_cast<float4 *>(Q + (int64_t)hot_items[s] * d + 4 * pc) = v;
 }
 
 static BprView make_view(gorse_b200_cf *cf)
@@ -737,7 +704,7 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
             const size_t need = (size_t)GB_HOTQ_REGIONS * region_cap * 3;
             if (cf->hotq.n < need) GB_TRY(cf->hotq.alloc(need));
             if (cf->hot_sorted.n < (size_t)2 * n_local + 2) GB_TRY(cf->hot_sorted.alloc((size_t)2 * n_local + 2));
-            if (cf->hot_ctr.n == 0) GB_TRY(cf->hot_ctr.alloc(GB_HOTQ_REGIONS * 2 + 5 * 1032));
+            if (cf->hot_ctr.n == 0) GB_TRY(cf->hot_ctr.alloc(GB_HOTQ_REGIONS * 2 + 4 * 1032));
             GB_CUDA(cudaMemsetAsync(cf->hot_ctr.p, 0, cf->hot_ctr.n * sizeof(unsigned), c->stream));
             hq.entries = cf->hotq.p;
             hq.counts = reinterpret_cast<unsigned long long *>(cf->hot_ctr.p);
@@ -750,11 +717,11 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
         else launch_epoch<false>(cf, v, hq, s0, n_local, mix64(seed), lr, reg);
         GB_LAUNCHED(c);
         if (use_hot) {
-            unsigned *hist = cf->hot_ctr.p + GB_HOTQ_REGIONS * 2, *begin = hist + 1032, *cursor = begin + 1032, *first_quad = cursor + 1032, *pending = first_quad + 1032;
+            unsigned *hist = cf->hot_ctr.p + GB_HOTQ_REGIONS * 2, *begin = hist + 1032, *cursor = begin + 1032, *first_quad = cursor + 1032;
             const int nh = cf->n_hot;
             // stale overlapping updates of one row are stable while lr * curvature * overlap stays well below 2;
             // scale the cap with 1/lr around the measured-safe 512 at the reference's default lr = 0.05
-            unsigned cap = (unsigned)std::min(4096.0f, std::max(32.0f, GB_HOT_ROW_CONCURRENCY * 0.05f / std::max(lr, 1e-6f)));
+            unsigned cap = (unsigned)std::min(1024.0f, std::max(32.0f, GB_HOT_ROW_CONCURRENCY * 0.05f / std::max(lr, 1e-6f)));
             if (const char *e = getenv("GORSE_B200_HOT_ROW_CONCURRENCY")) { int x = atoi(e); if (x > 0) cap = (unsigned)x; }
             // quad budget: what the machine holds at this kernel's occupancy (2-3 CTAs of 64 quads per SM)
             const unsigned quad_budget = (unsigned)c->sm_count * 3u * 64u;
@@ -775,9 +742,9 @@ int32_t gorse_b200_bpr_epoch(gorse_b200_cf *cf, float lr, float reg, int64_t n_s
                 case 4: hk = bpr_hot_apply_kernel<4>; break;
                 default: hk = bpr_hot_apply_kernel<8>; break;
             }
-            hk<<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg, pending);
+            hk<<<hg, 256, 0, c->stream>>>(v, nh, begin, first_quad, cf->hot_sorted.p, lr, reg);
             GB_LAUNCHED(c);
-            hot_scatter_decay_kernel<<<div_up((int64_t)cf->n_hot * (cf->d / 4), 256), 256, 0, c->stream>>>(cf->Q.p, cf->d, cf->hot_items.p, cf->n_hot, cf->hot_pad, cf->hot.p, pending, log1pf(-lr * reg));
+            hot_scatter_kernel<<<div_up((int64_t)cf->n_hot * (cf->d / 4), 256), 256, 0, c->stream>>>(cf->Q.p, cf->d, cf->hot_items.p, cf->n_hot, cf->hot_pad, cf->hot.p);
             GB_LAUNCHED(c);
         }
     }

@@ -466,7 +466,8 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     // spread).  Aim for 4.5k: fewer than k with probability ~6e-6 (3.2k, the round-1 value, failed for ~2e-4 of the rows = 30
     // rows of a 151 552-row call, and each failed row costs a full exact scan: 9 ms per call against +3 ms of prune / re-rank
     // work for the longer candidate lists), still far below the CAP-slot candidate list.
-    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (4.5 * k) / mma::BN);
+    static const double margin = [] { const char *e = getenv("GORSE_B200_TOPK_MARGIN"); return e ? atof(e) : 4.5; }();   // A/B, removed once settled
+    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (margin * k) / mma::BN);
     m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
@@ -479,7 +480,8 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
     // queries are processed in chunks of one 256-row group per SM: the candidate lists stay modest and the download of a
     // finished chunk's results (copy stream) overlaps the next chunk's kernels
-    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM;
+    static const int chunk_mult = [] { const char *e = getenv("GORSE_B200_TOPK_CHUNK"); return e ? atoi(e) : 1; }();   // A/B
+    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM * chunk_mult;
     // work buffers live in the index and are reused by later searches (multi-GB cudaMalloc/cudaFree per call otherwise)
     DevBuf<__nv_bfloat16> &Qb = ix->w_qb;
     DevBuf<float> &eps = ix->w_eps, &cval = ix->w_cval, &theta = ix->w_theta;

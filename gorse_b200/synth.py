@@ -134,3 +134,19 @@ def conflict_free_triples(user_off, user_items, n_items, n, seed=0):
         used.add(j)
         out.append((int(u), i, j))
     return np.asarray(out, np.int32).reshape(-1, 3)
+
+
+def write_ncf(prefix, train, test, neg):
+    """Write (train, test, negatives) CSRs as the NCF files dataset.LoadDataFromBuiltIn reads (dataset/dataset.go:398-490):
+    `<prefix>.train.rating` ("user<TAB>item<TAB>rating<TAB>timestamp") and `<prefix>.test.negative`
+    ("(user,item)<TAB>neg<TAB>neg...")."""
+    (tr_off, tr_items), (te_off, te_items), (ng_off, ng_items) = train, test, neg
+    with open(prefix + ".train.rating", "w") as f:
+        for u in range(len(tr_off) - 1):
+            for i in tr_items[tr_off[u]:tr_off[u + 1]]:
+                f.write(f"{u}\t{int(i)}\t1\t0\n")
+    with open(prefix + ".test.negative", "w") as f:
+        for u in range(len(te_off) - 1):
+            for i in te_items[te_off[u]:te_off[u + 1]]:
+                f.write(f"({u},{int(i)})" + "".join(f"\t{int(x)}" for x in ng_items[ng_off[u]:ng_off[u + 1]]) + "\n")
+    return prefix + ".train.rating", prefix + ".test.negative"

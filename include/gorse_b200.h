@@ -358,6 +358,20 @@ int32_t gorse_b200_vecdb_query(gorse_b200_vecdb *db, int64_t nq, const float *q_
                                const int32_t *categories, int32_t n_categories, int32_t topk, int64_t *slots_out, float *scores_out,
                                int32_t *count_out);
 
+/* ------------------------------------------------------------------------------------------
+ * NCF-format datasets: dataset.LoadDataFromBuiltIn (dataset/dataset.go:398-490), the loader `gorse-bench cf`
+ * (gorse_b200/csrc/gorse_bench_cf.cpp; BASELINE configs[0]) feeds the model with.  Host code.
+ *   train file  "user<TAB>item[<TAB>...]" per line (loadTrain :420-453)
+ *   test file   "(user,item)<TAB>neg<TAB>neg..." per line (loadTest :455-490), may be NULL
+ * gorse_b200_ncf_get fills CSR arrays sized from gorse_b200_ncf_shape (offsets n_users + 1); any pointer may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct gorse_b200_ncf gorse_b200_ncf;
+int32_t gorse_b200_ncf_load(const char *train_path, const char *test_path, gorse_b200_ncf **out);
+int32_t gorse_b200_ncf_shape(const gorse_b200_ncf *d, int32_t *n_users, int32_t *n_items, int64_t *n_train, int64_t *n_test, int64_t *n_neg);
+int32_t gorse_b200_ncf_get(const gorse_b200_ncf *d, int64_t *train_off, int32_t *train_items, int64_t *test_off, int32_t *test_items,
+                           int64_t *neg_off, int32_t *neg_items);
+int32_t gorse_b200_ncf_free(gorse_b200_ncf *d);
+
 #ifdef __cplusplus
 }
 #endif
