@@ -463,11 +463,11 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     const int64_t n_pad = (ix->n + mma::BN - 1) / mma::BN * mma::BN;
     const int n_tiles = (int)(n_pad / mma::BN);
     // sample size: the R_TOP-th best of m random columns leaves on average R_TOP * N / m columns above it (Gamma(R_TOP)
-    // spread).  Aim for 4.5k: fewer than k with probability ~6e-6 (3.2k, the round-1 value, failed for ~2e-4 of the rows = 30
-    // rows of a 151 552-row call, and each failed row costs a full exact scan: 9 ms per call against +3 ms of prune / re-rank
-    // work for the longer candidate lists), still far below the CAP-slot candidate list.
-    static const double margin = [] { const char *e = getenv("GORSE_B200_TOPK_MARGIN"); return e ? atof(e) : 4.5; }();   // A/B, removed once settled
-    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (margin * k) / mma::BN);
+    // spread).  Aim for 3.2k per column half: fewer than k with probability ~2e-4, and the HALF_CAP-slot candidate list
+    // overflows with probability ~1e-5.  (Round 2 tried 4.5k and 6k to get rid of the ~30 fallback rows per 151 552-row call:
+    // the lists, already inflated 1.35x by the -2 eps on theta, then overflow for 1 % / 20 % of the rows and the exact
+    // fallback takes over: 398 ms / 4.6 s per call instead of 68 ms.  profiles/r02_topk_margin_chunk.md.)
+    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (3.2 * k) / mma::BN);
     m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
@@ -478,10 +478,11 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
 
     CUtensorMap map_b;
     GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
-    // queries are processed in chunks of one 256-row group per SM: the candidate lists stay modest and the download of a
-    // finished chunk's results (copy stream) overlaps the next chunk's kernels
-    static const int chunk_mult = [] { const char *e = getenv("GORSE_B200_TOPK_CHUNK"); return e ? atoi(e) : 1; }();   // A/B
-    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM * chunk_mult;
+    // queries are processed in chunks of four 256-row groups per SM so that the candidate lists stay modest (one group per SM
+    // with the downloads of finished chunks overlapped was measured slower, 88.8 vs 68.5 ms per 151 552-row call: every chunk
+    // pays a kernel tail, a host sync for the fallback count and its own fallback launches); a finished chunk is downloaded
+    // on the copy stream while the next one computes
+    const int64_t chunk = (int64_t)c->sm_count * mma::TILES_M * mma::BM * 4;
     // work buffers live in the index and are reused by later searches (multi-GB cudaMalloc/cudaFree per call otherwise)
     DevBuf<__nv_bfloat16> &Qb = ix->w_qb;
     DevBuf<float> &eps = ix->w_eps, &cval = ix->w_cval, &theta = ix->w_theta;
