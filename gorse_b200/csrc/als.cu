@@ -434,6 +434,186 @@ als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_
     }
 }
 
+// ---- lane-group form with BLOCKED staging (round 2) ------------------------------------------------------------------
+// Same arithmetic as als_rows_group_kernel (B = 1), but the gathered rows are staged one block of G coordinates at a time
+// instead of whole: n * (G+1) floats per row in shared memory instead of n * (D+1).  The whole-row version held 33 KB (rows up
+// to 32 entries, two rows per warp) / 49.5 KB (rows up to 96 entries) per warp next to the 64 KB copy of S, i.e. 3-4 warps per
+// SM, and each of those warps runs a dependent shuffle chain per coordinate: 2.3 + 3.0 ms per half-sweep for 7 % of the rows
+// (profiles/r02_launches_c3.md).  Lane j of the group owns coordinate i*G + j of block i, so a block is exactly what the group
+// works on at a time:
+//   pass A  per sub-range of G entries and per block: stage G x G floats, partial_tt += x_i * y (registers, one per entry of
+//           the sub-range), h_i, c_i column sums; the partials are reduced across the group once per sub-range -> pred;
+//   sweep   per block: stage all n entries of the block, then the G coordinates as before.
+// Every entry is staged once per pass, as before (in G*4-byte pieces instead of whole rows).
+template <int G, int E, int KPL>
+__global__ void __launch_bounds__(512)
+als_rows_group_blocked_kernel(float *X, const float *Y, const int64_t *off, const int32_t *idx, const float *S, float reg, float w,
+                              const int32_t *row_ids, int32_t n_rows)
+{
+    constexpr int D = G * KPL, NG = 32 / G, GP = G + 1, G4 = G / 4;
+    constexpr int YS = E * G * GP + (G < 32 ? G : 0);      // floats per lane group (padded so that groups start G banks apart)
+    extern __shared__ float smem[];
+    float *Ss = smem;                                   // [D][D]
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int grp = lane / G, j = lane % G;
+    float *ys = smem + D * D + (size_t)(wid * NG + grp) * YS;
+    for (int e = threadIdx.x; e < D * D; e += blockDim.x) Ss[e] = S[e];
+    __syncthreads();
+    const float omw = 1.0f - w;
+    const int32_t stride = gridDim.x * nw * NG;
+    for (int32_t base = (blockIdx.x * nw + wid) * NG; base < n_rows; base += stride) {   // warp-uniform trip count
+        const int32_t slot = base + grp;
+        const bool act = slot < n_rows;
+        int32_t r = 0;
+        int n = 0;
+        int64_t o = 0;
+        if (act) { r = row_ids[slot]; o = off[r]; n = (int)(off[r + 1] - o); }
+        const int nmax = __reduce_max_sync(0xffffffffu, n);
+        // this lane's entries t = j + e*G: their row pointers
+        const float *yrow[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) yrow[e] = (j + e * G < n) ? Y + (int64_t)__ldg(idx + o + j + e * G) * D : Y;
+        float x[KPL], g[KPL], h[KPL], cw[KPL], inv[KPL], pred[E];
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            x[i] = act ? X[(int64_t)r * D + i * G + j] : 0.f;
+            g[i] = 0.f; h[i] = 0.f; cw[i] = 0.f;
+        }
+        // stage entries [t0, t0 + cnt) of block i: the group's lanes walk the cnt * G/4 float4 pieces; entry t comes from lane t % G
+        auto stage = [&](int i, int e0, int e1) {
+#pragma unroll
+            for (int e = e0; e < e1; e++) {
+                if (e * G >= nmax) break;                       // warp-uniform
+#pragma unroll
+                for (int c = j; c < G * G4; c += G) {
+                    const int tt = c / G4, q = c - tt * G4;     // entry e*G + tt, piece q
+                    const float *src = (const float *)__shfl_sync(0xffffffffu, (unsigned long long)yrow[e], tt, G);
+                    if (e * G + tt < n) {
+                        const float4 v = __ldg(reinterpret_cast<const float4 *>(src + i * G) + q);
+                        float *dst = ys + (e * G + tt) * GP + 4 * q;
+                        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                    }
+                }
+            }
+        };
+        // ---- pass A: pred_t = x . y_t (:661-663), h, c ----
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            pred[e] = 0.f;
+            if (e * G >= nmax) continue;                        // warp-uniform
+            float part[G];
+#pragma unroll
+            for (int tt = 0; tt < G; tt++) part[tt] = 0.f;
+#pragma unroll 1
+            for (int i = 0; i < KPL; i++) {
+                __syncwarp();
+                stage(i, e, e + 1);
+                __syncwarp();
+                float xi = x[0], hi = 0.f, ci = 0.f;
+#pragma unroll
+                for (int ii = 1; ii < KPL; ii++) if (i == ii) xi = x[ii];
+#pragma unroll
+                for (int tt = 0; tt < G; tt++) {
+                    if (e * G + tt >= nmax) break;              // warp-uniform
+                    if (e * G + tt < n) {
+                        const float y = ys[(e * G + tt) * GP + j];
+                        part[tt] = fmaf(xi, y, part[tt]);
+                        hi += y;
+                        ci = fmaf(y, y, ci);
+                    }
+                }
+#pragma unroll
+                for (int ii = 0; ii < KPL; ii++) if (i == ii) { h[ii] += hi; cw[ii] += ci; }
+            }
+#pragma unroll
+            for (int tt = 0; tt < G; tt++) {
+                if (e * G + tt >= nmax) break;
+                const float s = group_sum<G>(part[tt]);
+                if (tt == j) pred[e] = s;
+            }
+        }
+        // g = S x (S symmetric: row m is column m), cw = (1-w) c + w S_kk, inv = 1 / (cw + reg)
+#pragma unroll
+        for (int mi = 0; mi < KPL; mi++) {
+#pragma unroll 1
+            for (int mj = 0; mj < G; mj++) {
+                const float xm = __shfl_sync(0xffffffffu, x[mi], mj, G);
+                const float *srow = Ss + (mi * G + mj) * D + j;
+#pragma unroll
+                for (int i = 0; i < KPL; i++) g[i] = fmaf(xm, srow[i * G], g[i]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < KPL; i++) {
+            const int k = i * G + j;
+            cw[i] = omw * cw[i] + w * Ss[k * D + k];
+            inv[i] = 1.0f / (cw[i] + reg);
+        }
+        // ---- the sweep, block by block ----
+#pragma unroll
+        for (int fi = 0; fi < KPL; fi++) {
+            __syncwarp();
+            stage(fi, 0, E);
+            __syncwarp();
+#pragma unroll 1
+            for (int jo = 0; jo < G; jo++) {
+                float ye[E], red = 0.f;
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    const int t = j + e * G;
+                    ye[e] = t < n ? ys[t * GP + jo] : 0.f;
+                    red = fmaf(pred[e], ye[e], red);
+                }
+                red = group_sum<G>(red);
+                const float num = (h[fi] - omw * red) + (x[fi] * cw[fi] - w * g[fi]);
+                const float xn = num * inv[fi];
+                const float dl = __shfl_sync(0xffffffffu, xn - x[fi], jo, G);
+                if (j == jo) x[fi] = xn;
+                const float *srow = Ss + (fi * G + jo) * D + j;
+#pragma unroll
+                for (int i = 0; i < KPL; i++) g[i] = fmaf(dl, srow[i * G], g[i]);
+#pragma unroll
+                for (int e = 0; e < E; e++) pred[e] = fmaf(dl, ye[e], pred[e]);
+            }
+        }
+        if (act) {
+#pragma unroll
+            for (int i = 0; i < KPL; i++) X[(int64_t)r * D + i * G + j] = x[i];
+        }
+        __syncwarp();   // the next row's staging must not overtake this row's column reads
+    }
+}
+
+template <int G, int E, int KPL>
+static int32_t launch_group_blocked(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
+                                    const int32_t *rows, int32_t n_rows)
+{
+    gorse_b200_ctx *c = cf->ctx;
+    constexpr int D = G * KPL, YS = E * G * (G + 1) + (G < 32 ? G : 0);
+    const size_t s_bytes = sizeof(float) * D * D, per_warp = sizeof(float) * (32 / G) * YS;
+    const int warps = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024 - s_bytes) / per_warp));
+    const size_t sm = s_bytes + warps * per_warp;
+    const int groups_per_cta = warps * (32 / G);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_rows + groups_per_cta - 1) / groups_per_cta, (int64_t)c->sm_count));
+    auto *k = als_rows_group_blocked_kernel<G, E, KPL>;
+    GB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    k<<<grid, 32 * warps, sm, c->stream>>>(X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows);
+    GB_LAUNCHED(c);
+    return GORSE_B200_OK;
+}
+
+template <int G, int E>
+static int32_t launch_group_blocked_d(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
+                                      const int32_t *rows, int32_t n_rows)
+{
+    switch (cf->d / 32) {
+        case 1: return launch_group_blocked<G, E, 32 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+        case 2: return launch_group_blocked<G, E, 64 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+        case 3: return launch_group_blocked<G, E, 96 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+        default: return launch_group_blocked<G, E, 128 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
+    }
+}
+
 // ---- Gram form for rows too long to stage ---------------------------------------------------
 // eALS over f for one row is exactly one Gauss-Seidel sweep on  A x = h  with
 //     A = (1-w) * G + w * S + reg * I,   G = sum_{t in R} y_t y_t^T,   h = sum_{t in R} y_t
@@ -735,8 +915,16 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
         if (grouped && k != GB_ALS_LONG) {
             const RowClass rc = kRowClasses[k];
             if (rc.kind == 0) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
-            else if (rc.G == 16) GB_TRY((launch_group_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-            else GB_TRY((launch_group_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else {
+                static const bool whole = [] { const char *e = getenv("GORSE_B200_ALS_WHOLE_ROWS"); return e && atoi(e) == 1; }();   // A/B
+                if (rc.G == 16) {
+                    if (whole) GB_TRY((launch_group_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+                    else GB_TRY((launch_group_blocked_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+                } else {
+                    if (whole) GB_TRY((launch_group_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+                    else GB_TRY((launch_group_blocked_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+                }
+            }
             continue;
         }
         // one warp per row; the long class without a Gram form (d > 128) gathers from L2 without staging

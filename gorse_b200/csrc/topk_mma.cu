@@ -53,21 +53,51 @@ struct Params {
     int32_t *cand_cnt;    // [nq][2] pushes per column half (may exceed HALF_CAP)
     float *theta;         // [nq][2] threshold used by each half
     float *dbg;           // optional dense [nq][n_tiles*128] score dump (tests)
+    const __nv_bfloat16 *qb;   // ATM: the bf16 query mirror [nq_pad][Kp] (read by the threads that own the rows)
+    int64_t nq_pad;
 };
 
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// three-input max (Blackwell FMNMX3)
+__device__ __forceinline__ float max3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// max of 32 accumulator columns: a balanced tree of 3-input maxima, 16 instructions, depth 4
+__device__ __forceinline__ float max32(const uint32_t (&v)[32])
+{
+#define GB_F(i) __uint_as_float(v[i])
+    const float a0 = max3(GB_F(0), GB_F(1), GB_F(2)), a1 = max3(GB_F(3), GB_F(4), GB_F(5)), a2 = max3(GB_F(6), GB_F(7), GB_F(8)),
+                a3 = max3(GB_F(9), GB_F(10), GB_F(11)), a4 = max3(GB_F(12), GB_F(13), GB_F(14)), a5 = max3(GB_F(15), GB_F(16), GB_F(17)),
+                a6 = max3(GB_F(18), GB_F(19), GB_F(20)), a7 = max3(GB_F(21), GB_F(22), GB_F(23)), a8 = max3(GB_F(24), GB_F(25), GB_F(26)),
+                a9 = max3(GB_F(27), GB_F(28), GB_F(29));
+#undef GB_F
+    const float b0 = max3(a0, a1, a2), b1 = max3(a3, a4, a5), b2 = max3(a6, a7, a8), b3 = max3(a9, __uint_as_float(v[30]), __uint_as_float(v[31]));
+    return fmaxf(max3(b0, b1, b2), b3);
+}
+
 // (An epilogue testing 8 columns per branch with a 3-input max tree was measured in round 2: stage-1 fraction 0.515 vs
 // 0.565 with 4 columns per branch; removed.)
-template <int STAGES>
+// ATM (round 2): the query tiles live in TENSOR MEMORY instead of shared memory.  With both operands in shared memory every
+// M128 N128 K16 instruction reads 8 KB of operands per 64 tensor cycles -- exactly the 128 B/clk of the SM's shared memory,
+// which the TMA writes of the next B tile need as well: the pipe ran at 39 % (profiles/r01_topk_mma_final.md), the epilogue
+// warps mostly spun on t_full.  A (a 256-row query group, reused for all ~8 000 B tiles) is written once per group by the
+// threads that own those rows (tcgen05.st: thread = lane = row) and the MMA takes it from there (the "TS" form): operand
+// traffic per instruction halves.  TMEM map: accumulator of tile m at columns [128 m, 128 m + 128); A of tile m at
+// 256 + m * Kp/2 (two bf16 per column).  One accumulator per tile instead of two stages: the two query tiles ping-pong
+// (tile 1's MMAs run while tile 0's accumulator is drained), which overlaps MMA and epilogue exactly like two stages did.
+template <int STAGES, bool DBG, bool ATM>
 __global__ void __launch_bounds__(THREADS, 1)
 topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params P)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *smem_a = smem;                                              // [TILES_M][kb] tiles
-    uint8_t *smem_b = smem_a + (size_t)TILES_M * P.kb * TILE_BYTES;      // [STAGES][kb] tiles
+    uint8_t *smem_a = smem;                                              // [TILES_M][kb] tiles (none when ATM)
+    uint8_t *smem_b = smem_a + (ATM ? 0 : (size_t)TILES_M * P.kb * TILE_BYTES);      // [STAGES][kb] tiles
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + (size_t)STAGES * P.kb * TILE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *a_full = bars + 2 * STAGES, *a_empty = a_full + 1;
     uint64_t *t_full = a_empty + 1, *t_empty = t_full + 2;
@@ -76,9 +106,9 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(a_full, 1);
+        mbar_init(a_full, ATM ? EPI_WARPS / 2 : 1);   // ATM: the 8 warps that write A arrive
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], EPI_WARPS); }
+        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], ATM ? EPI_WARPS / 2 : EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -96,14 +126,16 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             uint32_t it = 0, ag = 0;
             for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
-                mbar_wait(a_empty, (ag & 1) ^ 1);  // MMA of the previous group no longer reads A
-                mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
-                for (int m = 0; m < TILES_M; m++)
-                    for (int kb = 0; kb < P.kb; kb++)
-                        tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
+                if constexpr (!ATM) {
+                    mbar_wait_backoff(a_empty, (ag & 1) ^ 1);  // MMA of the previous group no longer reads A
+                    mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
+                    for (int m = 0; m < TILES_M; m++)
+                        for (int kb = 0; kb < P.kb; kb++)
+                            tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
+                }
                 for (int t = 0; t < total_tiles; t++, it++) {
                     const int s = it % STAGES;
-                    mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    mbar_wait_backoff(&empty[s], ((it / STAGES) & 1) ^ 1);
                     mbar_expect_tx(&full[s], (uint32_t)P.kb * TILE_BYTES);
                     const int bt = t < P.n_tiles ? t : t - P.n_tiles;
                     for (int kb = 0; kb < P.kb; kb++)
@@ -116,7 +148,28 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             uint32_t it = 0, ag = 0, at = 0;
             for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
-                mbar_wait(a_full, ag & 1);
+                mbar_wait_backoff(a_full, ag & 1);
+                if constexpr (ATM) {
+                    const uint32_t a_col0 = 2u * BN;                       // A tiles start after the two accumulators
+                    for (int t = 0; t < total_tiles; t++, it++, at++) {
+                        const int s = it % STAGES;
+                        mbar_wait(&full[s], (it / STAGES) & 1);
+                        for (int m = 0; m < TILES_M; m++) {
+                            mbar_wait(&t_empty[m], (at & 1) ^ 1);          // tile m's accumulator was drained (step at - 1)
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            const uint32_t d = tmem_base + (uint32_t)(m * BN);
+                            const uint32_t a = tmem_base + a_col0 + (uint32_t)(m * P.kb * (BK / 2));
+                            for (int kb = 0; kb < P.kb; kb++) {
+                                const uint8_t *tb = smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES;
+#pragma unroll
+                                for (int k = 0; k < BK / 16; k++)
+                                    umma_bf16_ts(d, a + (uint32_t)(kb * (BK / 2) + k * 8), umma_desc(tb, k * 32), IDESC, (kb | k) != 0);
+                            }
+                            umma_commit(&t_full[m]);
+                        }
+                        umma_commit(&empty[s]);      // B stage reusable once both tiles' MMAs retire
+                    }
+                } else {
                 for (int t = 0; t < total_tiles; t++, it++, at++) {
                     const int s = it % STAGES, as = at & 1;
                     mbar_wait(&t_empty[as], ((at >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
@@ -135,6 +188,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
                     umma_commit(&t_full[as]);    // both accumulators of this stage are complete
                 }
+                }
                 umma_commit(a_empty);
             }
         }
@@ -144,7 +198,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // sample, a valid if slightly looser bound), so the two halves never synchronise.
         const int ew = warp - 4, m = ew >> 3, half = (ew >> 2) & 1;
         const uint32_t lane_base = (uint32_t)((ew & 3) * 32) << 16;  // a warp may only touch its own 32 TMEM lanes
-        uint32_t at = 0;
+        uint32_t at = 0, at_g = 0;
         for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
             const int64_t row = (int64_t)(g * TILES_M + m) * BM + (ew & 3) * 32 + lane;
             const bool row_ok = row < P.nq;
@@ -154,32 +208,59 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int r = 0; r < R_TOP; r++) top[r] = -INFINITY;
             float theta = -INFINITY;
             int cnt = 0;
-            int32_t *ccol = P.cand_col + (row_ok ? row : 0) * CAP + half * HALF_CAP;
-            float *cval = P.cand_val + (row_ok ? row : 0) * CAP + half * HALF_CAP;
+            if constexpr (ATM) {
+                // this group's query rows -> tensor memory (the half-0 warps of each tile: thread = TMEM lane = row)
+                if (half == 0) {
+                    if (lane == 0) mbar_wait(a_empty, ((at_g & 1) ^ 1));   // the previous group's MMAs no longer read A
+                    __syncwarp();
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t *qrow = reinterpret_cast<const uint32_t *>(P.qb) + (row < P.nq_pad ? row : 0) * (int64_t)(P.kb * (BK / 2));
+                    const uint32_t a = tmem_base + lane_base + 2u * BN + (uint32_t)(m * P.kb * (BK / 2));
+                    for (int c0 = 0; c0 < P.kb * (BK / 2); c0 += 32) {
+                        uint32_t v[32];
+#pragma unroll
+                        for (int e = 0; e < 32; e += 4) {
+                            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(qrow + c0 + e));
+                            v[e] = u.x; v[e + 1] = u.y; v[e + 2] = u.z; v[e + 3] = u.w;
+                        }
+                        tmem_st32(a + c0, v);
+                    }
+                    tmem_st_wait();
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full);
+                }
+                at_g++;
+            }
+            // per-warp scratch row for the cooperative push (128 bytes)
+            float *scr = reinterpret_cast<float *>(tmem_slot + 4) + ew * 32;
+            const int64_t row0 = (int64_t)(g * TILES_M + m) * BM + (ew & 3) * 32;   // row of lane 0
             for (int t = 0; t < total_tiles; t++, at++) {
                 const int as = at & 1;
                 const bool sample = t < P.m_tiles;
-                if (t == P.m_tiles) theta = top[R_TOP - 1] - 2.f * eps;
+                if (t == P.m_tiles) theta = row_ok ? top[R_TOP - 1] - 2.f * eps : INFINITY;   // padding rows never hit
                 const int bt = t < P.n_tiles ? t : t - P.n_tiles;
-                mbar_wait(&t_full[as], (at >> 1) & 1);
+                if constexpr (ATM) mbar_wait(&t_full[m], at & 1);
+                else mbar_wait(&t_full[as], (at >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_base + lane_base + (uint32_t)((m * 2 + as) * BN);
+                const uint32_t acc = tmem_base + lane_base + (uint32_t)(ATM ? m * BN : (m * 2 + as) * BN);
 #pragma unroll 1
                 for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
                     uint32_t v[32];
-                    __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the data-dependent pushes
                     tmem_ld32(acc + c0, v);
                     const int64_t col0 = (int64_t)bt * BN + c0;
-                    if (P.dbg && row_ok && t < P.n_tiles) {
+                    if constexpr (DBG) {
+                        if (P.dbg && row_ok && t < P.n_tiles) {
 #pragma unroll
-                        for (int e = 0; e < 32; e++) P.dbg[row * ((int64_t)P.n_tiles * BN) + col0 + e] = __uint_as_float(v[e]);
+                            for (int e = 0; e < 32; e++) P.dbg[row * ((int64_t)P.n_tiles * BN) + col0 + e] = __uint_as_float(v[e]);
+                        }
                     }
                     if (sample) {
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
                             const float x = __uint_as_float(v[e]);
                             if (x > top[R_TOP - 1] && col0 + e < P.n) {
-                                // insertion into the sorted 8 best (rare after the first few hundred columns)
+                                // insertion into the sorted 16 best (rare after the first few hundred columns)
                                 float cur = x;
 #pragma unroll
                                 for (int r = 0; r < R_TOP; r++) {
@@ -189,28 +270,44 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 }
                             }
                         }
+                        __syncwarp();
                     } else {
-                        // one compare per 4 columns in the common case
+                        // One test per 32 columns, no divergent code: a hit is rare per row (~0.1 % of the columns) but a warp
+                        // holds 32 rows, so SOME lane hits in most batches -- the push is therefore done by the whole warp
+                        // for one hitting row at a time: the row's 32 scores go through a 128-byte scratch line so that lane e
+                        // sees column e, a ballot gives the push positions, the stores of a row are coalesced.
+                        const float mx = max32(v);
+                        unsigned hm = __ballot_sync(0xffffffffu, mx >= theta);
+                        while (hm) {
+                            const int L = __ffs(hm) - 1;
+                            hm &= hm - 1;
+                            if (lane == L) {
 #pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            const float mx = fmaxf(fmaxf(__uint_as_float(v[e]), __uint_as_float(v[e + 1])),
-                                                   fmaxf(__uint_as_float(v[e + 2]), __uint_as_float(v[e + 3])));
-                            if (mx >= theta) {
-#pragma unroll
-                                for (int f = 0; f < 4; f++) {
-                                    const float x = __uint_as_float(v[e + f]);
-                                    if (x >= theta && col0 + e + f < P.n && row_ok) {
-                                        if (cnt < HALF_CAP) { ccol[cnt] = (int32_t)(col0 + e + f); cval[cnt] = x; }
-                                        cnt++;
-                                    }
+                                for (int e = 0; e < 32; e += 4)
+                                    *reinterpret_cast<uint4 *>(scr + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+                            }
+                            __syncwarp();
+                            const float x = scr[lane];
+                            const float thL = __shfl_sync(0xffffffffu, theta, L);
+                            const int cntL = __shfl_sync(0xffffffffu, cnt, L);
+                            const bool push = x >= thL && col0 + lane < P.n;
+                            const unsigned pm = __ballot_sync(0xffffffffu, push);
+                            if (push) {
+                                const int pos = cntL + __popc(pm & ((1u << lane) - 1));
+                                if (pos < HALF_CAP) {
+                                    const int64_t o = (row0 + L) * CAP + half * HALF_CAP + pos;
+                                    P.cand_col[o] = (int32_t)(col0 + lane);
+                                    P.cand_val[o] = x;
                                 }
                             }
+                            if (lane == L) cnt += __popc(pm);
+                            __syncwarp();
                         }
                     }
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&t_empty[as]);
+                if (lane == 0) mbar_arrive(ATM ? &t_empty[m] : &t_empty[as]);
             }
             if (row_ok) { P.cand_cnt[2 * row + half] = cnt; P.theta[2 * row + half] = theta; }
         }
@@ -471,10 +568,11 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
-    const size_t a_bytes = (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;
+    static const bool atm = [] { const char *e = getenv("GORSE_B200_TOPK_ATM"); return !(e && *e == '0'); }();   // A/B: =0 keeps A in shared memory
+    const size_t a_bytes = atm ? 0 : (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;
     int stages = (int)std::min<size_t>(4, (200 * 1024 - a_bytes) / b_stage);
     if (stages < 2) { set_error("search_mma: Kp = %d does not fit", kp); return GORSE_B200_ERR_UNSUPPORTED; }
-    const size_t smem = a_bytes + (size_t)stages * b_stage + 1024 /*align*/ + 256 /*barriers*/;
+    const size_t smem = a_bytes + (size_t)stages * b_stage + 1024 /*align*/ + 256 /*barriers*/ + (size_t)mma::EPI_WARPS * 128 /*push scratch*/;
 
     CUtensorMap map_b;
     GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
@@ -502,7 +600,12 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         return done(st);
     else { ix->w_cq = cq; ix->w_kp = kp; }
     const int64_t fl_off = ix->w_cq;  // the fallback counter sits after the list
-    auto kern = stages >= 4 ? mma::topk_mma_kernel<4> : stages == 3 ? mma::topk_mma_kernel<3> : mma::topk_mma_kernel<2>;
+    const bool dbg = ix->dbg_scores != nullptr;   // the dense score dump of the test hook is compiled out of the production kernel
+    auto pick = [&](auto s4, auto s3, auto s2) { return stages >= 4 ? s4 : stages == 3 ? s3 : s2; };
+    auto kern = atm ? (dbg ? pick(mma::topk_mma_kernel<4, true, true>, mma::topk_mma_kernel<3, true, true>, mma::topk_mma_kernel<2, true, true>)
+                           : pick(mma::topk_mma_kernel<4, false, true>, mma::topk_mma_kernel<3, false, true>, mma::topk_mma_kernel<2, false, true>))
+                    : (dbg ? pick(mma::topk_mma_kernel<4, true, false>, mma::topk_mma_kernel<3, true, false>, mma::topk_mma_kernel<2, true, false>)
+                           : pick(mma::topk_mma_kernel<4, false, false>, mma::topk_mma_kernel<3, false, false>, mma::topk_mma_kernel<2, false, false>));
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("search_mma smem attr: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
     for (int64_t off = 0; off < nq; off += cq) {
@@ -516,7 +619,7 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         if ((st = make_map(&map_a, Qb.p, n_this_pad, kp))) return done(st);
         mma::Params P;
         P.n = ix->n; P.n_tiles = n_tiles; P.m_tiles = m_tiles; P.kb = kb; P.nq = n_this; P.n_groups = (int)(n_this_pad / 256);
-        P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores;
+        P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores; P.qb = Qb.p; P.nq_pad = n_this_pad;
         const int grid = std::min(P.n_groups, c->sm_count);
         if (!ix->ev0) { cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1); }
         cudaEventRecord(ix->ev0, c->stream);

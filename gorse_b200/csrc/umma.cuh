@@ -36,6 +36,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
             : "memory");
     }
 }
+// the same wait for warps that are NOT on the critical path of the SM's issue slots (TMA producer, MMA issuer): back off
+// between polls.  The two single-thread roles of topk_mma_kernel spent 5 G warp instructions per launch (15 % of all issued)
+// spinning next to the epilogue warps that the kernel is bound by (profiles/r02_topk_epilogue.md).
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t *bar, uint32_t parity)
+{
+    uint32_t done = 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(s32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(40);
+    }
+}
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s32(dst)),
@@ -57,6 +75,30 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// A operand from tensor memory (K-major only: "A from TMEM can't be transposed", CUTLASS SM100_MMA_F16BF16_TS): lane = row of A,
+// 32-bit column c holds elements 2c, 2c+1 of the row's K slice; the instruction reads K = 16 elements = 8 columns
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane <- registers (the mirror of tmem_ld32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+          "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]),
+          "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");

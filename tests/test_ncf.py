@@ -63,7 +63,10 @@ def test_gorse_bench_cf_on_an_ml100k_surrogate(gb, orc, tmp_path, model):
     out = subprocess.run([exe, "--train", a, "--test", b, "--model", model, "--factors", "16", "--epochs", "30", "--seed", "5", *extra],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "| train |    943 |   1682 |        100000 |" in out.stdout
+    Uf, If, trf, tef, ngf = gb.load_ncf(a, b)     # the dictionary sizes are what the FILES say (ids never drawn do not exist)
+    assert Uf == U and If <= I and trf[0][-1] == 100_000
+    assert f"| train | {Uf:6d} | {If:6d} | {100000:13d} |" in out.stdout
+    I = If
     row = re.search(r"\| (BPR|ALS)\s+\|\s+([0-9.]+) \|\s+([0-9.]+) \|\s+([0-9.]+) \|\s+(\d+)", out.stdout)
     assert row and row.group(1) == model.upper() and int(row.group(5)) == 30
     ndcg = float(row.group(2))
