@@ -146,12 +146,12 @@ __global__ void gram_generic_kernel(const float *X, int32_t rows, int d, const i
 }
 
 // fixed-order reduction of the per-CTA partials: deterministic run to run
-__global__ void gram_reduce_kernel(const float *partial, int n_parts, int dd, float *S)
+__global__ void gram_reduce_kernel(const float *partial, int n_parts, int dd, int64_t stride, float *S)
 {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= dd) return;
     float s = 0.f;
-    for (int p = 0; p < n_parts; p++) s += partial[(int64_t)p * dd + e];
+    for (int p = 0; p < n_parts; p++) s += partial[(int64_t)p * stride + e];
     S[e] = s;
 }
 
@@ -671,16 +671,34 @@ __global__ void __launch_bounds__(256) als_chunk_gram_kernel(const float *Y, int
     }
 }
 
-// one CTA per long row: sum its chunk partials in order (deterministic), build A, one Gauss-Seidel sweep by warp 0
+// partial[first chunk of the row] = sum of the row's chunk partials, in chunk order (deterministic); grid (rows, element tiles).
+// Without it one CTA of als_solve_kernel walked all chunks of its row alone: the hottest item of C3 has 232 chunks = 15 MB,
+// and that single CTA was the tail of the whole kernel.
+__global__ void __launch_bounds__(256) als_partial_reduce_kernel(const int32_t *row_chunk0, int stride4, float *partial)
+{
+    const int c0 = row_chunk0[blockIdx.x], c1 = row_chunk0[blockIdx.x + 1];
+    if (c1 - c0 <= 1) return;
+    const int e = blockIdx.y * 256 + threadIdx.x;
+    if (e >= stride4) return;
+    float4 *p = reinterpret_cast<float4 *>(partial);
+    float4 acc = p[(int64_t)c0 * stride4 + e];
+    for (int c = c0 + 1; c < c1; c++) {
+        const float4 v = p[(int64_t)c * stride4 + e];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    p[(int64_t)c0 * stride4 + e] = acc;
+}
+
+// one CTA per long row: its (already summed) partial -> A, one Gauss-Seidel sweep by warp 0
 __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const float *S, float reg, float w, const int32_t *rows,
-                                                        const int32_t *row_chunk0, const float *partial)
+                                                        const int32_t *row_chunk0, const float *partial, int reduced)
 {
     extern __shared__ float sm[];
     float *A = sm;                 // [d][d+1]
     float *h = A + d * (d + 1);    // [d]
     float *x = h + d;              // [d]
     const int r = rows[blockIdx.x];
-    const int c0 = row_chunk0[blockIdx.x], c1 = row_chunk0[blockIdx.x + 1];
+    const int c0 = row_chunk0[blockIdx.x], c1 = reduced ? c0 + 1 : row_chunk0[blockIdx.x + 1];
     const int dd = d * d, stride = dd + d;
     const float omw = 1.0f - w;
     for (int e = threadIdx.x; e < dd; e += blockDim.x) {
@@ -718,10 +736,27 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
 
 // S = sum over rows with >= 1 feedback of x x^T.  `X`, `off` and `rows` describe THIS RANK's row range (off is the rank's
 // rebased offsets); in a distributed context the d x d partial sums are all-reduced, so every rank ends with the same bits.
-static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const int64_t *off)
+static int32_t run_gram(gorse_b200_cf *cf, int side, const float *X_base, const float *X, int32_t rows, const int64_t *off)
 {
     gorse_b200_ctx *c = cf->ctx;
     const int d = cf->d, dd = d * d;
+    static const bool no_tc = [] { const char *e = getenv("GORSE_B200_ALS_NO_TC"); return e && atoi(e) == 1; }();   // A/B runs
+    if (d == 128 && !no_tc) {
+        // S = sum of x x^T over the rows with feedback: the same tensor-core kernel as the row Grams, fed with the list of
+        // those rows in chunks of GB_ALS_CHUNK (als_gram_tc.cu); the chunk partials are summed in order (deterministic)
+        const int nc = cf->als_s_chunks[side];
+        const size_t need = (size_t)std::max(nc, 1) * (dd + d);
+        if (cf->scratch.n < need) GB_TRY(cf->scratch.alloc(need));
+        if (nc > 0) GB_TRY(als_chunk_gram_tc(c, X_base, cf->als_s_rows[side].p, cf->als_s_begin[side].p, cf->als_s_len[side].p, nc, cf->scratch.p));
+        else GB_CUDA(cudaMemsetAsync(cf->scratch.p, 0, sizeof(float) * need, c->stream));
+        gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, c->stream>>>(cf->scratch.p, std::max(nc, 1), dd, (int64_t)dd + d, cf->gram.p);
+        GB_LAUNCHED(c);
+        if (c->world > 1) {
+            GB_NCCL_API(nc_api);
+            GB_NCCL(nc_api, AllReduce(cf->gram.p, cf->gram.p, (size_t)dd, ncclFloat32, ncclSum, c->comm, c->stream));
+        }
+        return GORSE_B200_OK;
+    }
     int parts = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)rows + 63) / 64, (int64_t)c->sm_count * 2));
     size_t need = (size_t)parts * dd;
     if (cf->scratch.n < need) GB_TRY(cf->scratch.alloc(need));
@@ -738,7 +773,7 @@ static int32_t run_gram(gorse_b200_cf *cf, const float *X, int32_t rows, const i
         gram_generic_kernel<<<parts, 256, 0, c->stream>>>(X, rows, d, off, cf->scratch.p);
     }
     GB_LAUNCHED(c);
-    gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, c->stream>>>(cf->scratch.p, parts, dd, cf->gram.p);
+    gram_reduce_kernel<<<(dd + 255) / 256, 256, 0, c->stream>>>(cf->scratch.p, parts, dd, (int64_t)dd, cf->gram.p);
     GB_LAUNCHED(c);
     if (c->world > 1) {
         GB_NCCL_API(nc);
@@ -834,6 +869,25 @@ static int32_t prepare_als(gorse_b200_cf *cf)
         const size_t need = (size_t)std::max(cf->als_n_chunks[0], cf->als_n_chunks[1]) * ((size_t)cf->d * cf->d + cf->d);
         if (need) GB_TRY(cf->als_partial.alloc(need));
     }
+    // rows with feedback of this rank's range (the rows S sums over, model.go:651,699), cut into chunks for the tensor-core Gram
+    for (int side = 0; side < 2 && cf->d == 128; side++) {
+        int32_t r_lo = 0, r_hi = 0;
+        shard_range(cf, side, r_lo, r_hi);
+        const int64_t *off = (side == 0 ? cf->h_user_off : cf->h_item_off).data() - r_lo;
+        std::vector<int32_t> rows, len;
+        std::vector<int64_t> begin;
+        for (int32_t r = r_lo; r < r_hi; r++) if (off[(size_t)r + 1] > off[r]) rows.push_back(r);
+        for (size_t p = 0; p < rows.size(); p += GB_ALS_CHUNK) { begin.push_back((int64_t)p); len.push_back((int32_t)std::min<size_t>(GB_ALS_CHUNK, rows.size() - p)); }
+        cf->als_s_chunks[side] = (int32_t)begin.size();
+        GB_TRY(cf->als_s_rows[side].alloc(rows.size()));
+        GB_TRY(cf->als_s_begin[side].alloc(begin.size()));
+        GB_TRY(cf->als_s_len[side].alloc(len.size()));
+        if (!rows.empty()) {
+            GB_CUDA(cudaMemcpy(cf->als_s_rows[side].p, rows.data(), sizeof(int32_t) * rows.size(), cudaMemcpyHostToDevice));
+            GB_CUDA(cudaMemcpy(cf->als_s_begin[side].p, begin.data(), sizeof(int64_t) * begin.size(), cudaMemcpyHostToDevice));
+            GB_CUDA(cudaMemcpy(cf->als_s_len[side].p, len.data(), sizeof(int32_t) * len.size(), cudaMemcpyHostToDevice));
+        }
+    }
     GB_CUDA(cudaFuncSetAttribute(als_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     GB_TRY(cf->gram.alloc((size_t)cf->d * cf->d));
     GB_CUDA(cudaFuncSetAttribute(als_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -908,13 +962,23 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
                 GB_LAUNCHED(c);
             }
             const size_t ssm = sizeof(float) * ((size_t)d * (d + 1) + 2 * d);
-            als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, rows, cf->als_row_chunk0[side].p, cf->als_partial.p);
+            const int reduced = (d * d + d) % 4 == 0;
+            if (reduced) {
+                als_partial_reduce_kernel<<<dim3(n_rows, div_up((d * d + d) / 4, 256)), 256, 0, c->stream>>>(cf->als_row_chunk0[side].p, (d * d + d) / 4, cf->als_partial.p);
+                GB_LAUNCHED(c);
+            }
+            als_solve_kernel<<<n_rows, 256, ssm, c->stream>>>(X, d, cf->gram.p, reg, w, rows, cf->als_row_chunk0[side].p, cf->als_partial.p, reduced);
             GB_LAUNCHED(c);
             continue;
         }
         if (grouped && k != GB_ALS_LONG) {
             const RowClass rc = kRowClasses[k];
-            if (rc.kind == 0) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
+            // A/B (round 2): rows with more than GORSE_B200_ALS_THREAD_MAX entries leave the thread-per-row kernel for a lane
+            // group of 8 / 16 lanes with blocked staging
+            static const int thread_max = [] { const char *e = getenv("GORSE_B200_ALS_THREAD_MAX"); return e ? atoi(e) : 4; }();
+            if (rc.kind == 0 && rc.max_n <= thread_max) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
+            else if (rc.kind == 0 && rc.max_n <= 8) GB_TRY((launch_group_blocked_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else if (rc.kind == 0) GB_TRY((launch_group_blocked_d<16, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else {
                 static const bool whole = [] { const char *e = getenv("GORSE_B200_ALS_WHOLE_ROWS"); return e && atoi(e) == 1; }();   // A/B
                 if (rc.G == 16) {
@@ -971,12 +1035,13 @@ extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alph
     gorse_b200_ctx *c = cf->ctx;
     const bool multi = c->world > 1;
     GB_TRY(prepare_als(cf));
-    DevBuf<float> pred;
-    GB_TRY(pred.alloc((size_t)std::max<int64_t>(1, std::max(cf->n_feedback, cf->n_item_feedback))));
+    // scratch kept in the model: a cudaMalloc/cudaFree pair per epoch costs more than some of the kernels of a C3 epoch
+    const size_t n_pred = (size_t)std::max<int64_t>(1, std::max(cf->n_feedback, cf->n_item_feedback));
+    if (cf->als_pred.n < n_pred) { cf->als_pred.free(); GB_TRY(cf->als_pred.alloc(n_pred)); }
+    DevBuf<float> &pred = cf->als_pred;
     int32_t st;
     auto done = [&](int32_t s) {
         cudaStreamSynchronize(c->stream);
-        pred.free();
         return s;
     };
     // Multi-rank: Q is replicated and P is range-sharded as for BPR.  The user half-sweep needs only Q, the item
@@ -996,10 +1061,10 @@ extern "C" int32_t gorse_b200_als_epoch(gorse_b200_cf *cf, float reg, float alph
     }
     // the row kernels index the offsets with GLOBAL row ids: hand them the rank's arrays shifted by the range start
     const int64_t *uoff = cf->user_off.p - cf->u_lo, *ioff = cf->item_off.p - cf->i_lo;
-    if ((st = run_gram(cf, cf->Q.p + (int64_t)cf->i_lo * cf->d, cf->i_hi - cf->i_lo, cf->item_off.p))) return done(st);
+    if ((st = run_gram(cf, 1, cf->Q.p, cf->Q.p + (int64_t)cf->i_lo * cf->d, cf->i_hi - cf->i_lo, cf->item_off.p))) return done(st);
     if ((st = run_rows(cf, 0, P, cf->Q.p, uoff, cf->user_items.p, reg, alpha, pred.p))) return done(st);
     if (multi && (st = exchange_shards(cf, 0, P))) return done(st);
-    if ((st = run_gram(cf, P + (int64_t)cf->u_lo * cf->d, cf->u_hi - cf->u_lo, cf->user_off.p))) return done(st);
+    if ((st = run_gram(cf, 0, P, P + (int64_t)cf->u_lo * cf->d, cf->u_hi - cf->u_lo, cf->user_off.p))) return done(st);
     if ((st = run_rows(cf, 1, cf->Q.p, P, ioff, cf->item_users.p, reg, alpha, pred.p))) return done(st);
     if (multi) {
         if ((st = exchange_shards(cf, 1, cf->Q.p))) return done(st);

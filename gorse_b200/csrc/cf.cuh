@@ -57,6 +57,7 @@ struct gorse_b200_cf {
     gb::DevBuf<unsigned> hot_ctr;              // queue counters, histogram, scan, cursors, ticket
     // ALS scratch
     gb::DevBuf<float> gram;      // d x d
+    gb::DevBuf<float> als_pred;  // eALS scratch: one prediction per entry of the longer CSR side, kept across epochs
     gb::DevBuf<float> scratch;   // per-row pred/res for long rows + partial grams
     gb::DevBuf<int32_t> als_rows[2][6];  // [side][class] row ids bucketed by length (built lazily; als.cu prepare_als)
     int32_t als_rows_n[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
@@ -66,6 +67,10 @@ struct gorse_b200_cf {
     gb::DevBuf<int32_t> als_chunk_row[2], als_chunk_len[2], als_row_chunk0[2];
     gb::DevBuf<int64_t> als_chunk_begin[2];
     gb::DevBuf<float> als_partial;
+    // rows with feedback, in chunks: what S = sum x x^T runs over on the tensor cores (d = 128)
+    int32_t als_s_chunks[2] = {0, 0};
+    gb::DevBuf<int32_t> als_s_rows[2], als_s_len[2];
+    gb::DevBuf<int64_t> als_s_begin[2];
     std::vector<int64_t> h_user_off, h_item_off;  // host copies of the offsets (bucketing, wave building)
 };
 

@@ -254,6 +254,8 @@ int32_t launch_exact_split(gorse_b200_index *ix, const float *d_q, const int64_t
     gorse_b200_ctx *c = ix->ctx;
     const int warps = 4;
     size_t sm = (size_t)warps * (2 * (size_t)k * 4 + (size_t)ix->d * 4);
+    // (round 2 tried finer segments to fill the machine with a handful of rows: the scan got faster but the merge, one
+    // warp re-scoring n_seg * k candidates per row, took 4x longer than what was saved)
     const int64_t seg_len = 16384;
     const int n_seg = (int)((ix->n + seg_len - 1) / seg_len);
     DevBuf<int32_t> p_idx, p_cnt;

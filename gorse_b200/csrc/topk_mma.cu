@@ -53,8 +53,6 @@ struct Params {
     int32_t *cand_cnt;    // [nq][2] pushes per column half (may exceed HALF_CAP)
     float *theta;         // [nq][2] threshold used by each half
     float *dbg;           // optional dense [nq][n_tiles*128] score dump (tests)
-    const __nv_bfloat16 *qb;   // ATM: the bf16 query mirror [nq_pad][Kp] (read by the threads that own the rows)
-    int64_t nq_pad;
 };
 
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
@@ -67,37 +65,30 @@ __device__ __forceinline__ float max3(float a, float b, float c)
     asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
 }
-// max of 32 accumulator columns: a balanced tree of 3-input maxima, 16 instructions, depth 4
-__device__ __forceinline__ float max32(const uint32_t (&v)[32])
-{
-#define GB_F(i) __uint_as_float(v[i])
-    const float a0 = max3(GB_F(0), GB_F(1), GB_F(2)), a1 = max3(GB_F(3), GB_F(4), GB_F(5)), a2 = max3(GB_F(6), GB_F(7), GB_F(8)),
-                a3 = max3(GB_F(9), GB_F(10), GB_F(11)), a4 = max3(GB_F(12), GB_F(13), GB_F(14)), a5 = max3(GB_F(15), GB_F(16), GB_F(17)),
-                a6 = max3(GB_F(18), GB_F(19), GB_F(20)), a7 = max3(GB_F(21), GB_F(22), GB_F(23)), a8 = max3(GB_F(24), GB_F(25), GB_F(26)),
-                a9 = max3(GB_F(27), GB_F(28), GB_F(29));
-#undef GB_F
-    const float b0 = max3(a0, a1, a2), b1 = max3(a3, a4, a5), b2 = max3(a6, a7, a8), b3 = max3(a9, __uint_as_float(v[30]), __uint_as_float(v[31]));
-    return fmaxf(max3(b0, b1, b2), b3);
-}
-
 // (An epilogue testing 8 columns per branch with a 3-input max tree was measured in round 2: stage-1 fraction 0.515 vs
 // 0.565 with 4 columns per branch; removed.)
-// ATM (round 2): the query tiles live in TENSOR MEMORY instead of shared memory.  With both operands in shared memory every
-// M128 N128 K16 instruction reads 8 KB of operands per 64 tensor cycles -- exactly the 128 B/clk of the SM's shared memory,
-// which the TMA writes of the next B tile need as well: the pipe ran at 39 % (profiles/r01_topk_mma_final.md), the epilogue
-// warps mostly spun on t_full.  A (a 256-row query group, reused for all ~8 000 B tiles) is written once per group by the
-// threads that own those rows (tcgen05.st: thread = lane = row) and the MMA takes it from there (the "TS" form): operand
-// traffic per instruction halves.  TMEM map: accumulator of tile m at columns [128 m, 128 m + 128); A of tile m at
-// 256 + m * Kp/2 (two bf16 per column).  One accumulator per tile instead of two stages: the two query tiles ping-pong
-// (tile 1's MMAs run while tile 0's accumulator is drained), which overlaps MMA and epilogue exactly like two stages did.
-template <int STAGES, bool DBG, bool ATM>
+// Round 2, what bounds this kernel (profiles/r02_topk_epilogue.md): NOT the epilogue's instruction count as round 1 read it
+// (a 3x lighter instruction stream changed nothing) and not the operand traffic of the MMAs (query tiles in tensor memory,
+// the "TS" form, were slower: one accumulator per tile instead of two stages).  A stage's accumulators are released when the
+// SLOWEST of the 16 epilogue warps is done, and what made warps slow was the push of the rare columns that clear the
+// threshold: ~1 hit per warp and 32-column batch on average, so per tile step SOME warp nearly always runs the push code
+// (divergent 4-column blocks in round 1, a shared-memory transpose + ballots, then a per-lane bit mask in round 2: ~100+
+// instructions at ~9 cycles each with 5 warps per scheduler), and the other 15 spin on t_full (12-20 % of all stall samples
+// sit on that one branch).  So: (1) both 32-column batches of a step are loaded into registers and the stage is released
+// BEFORE they are examined -- a warp with hits delays only itself, and the two accumulator stages average its load out;
+// (2) one 16-instruction max tree per 32 columns; a lane whose maximum clears theta walks back down the tree (4 + 3 + 3
+// compares for the usual single hit) and pushes into its own row's list, no cross-lane step (a 32-bit hit mask + scores
+// parked in local memory cost ~125 instructions per hitting batch: more than the 1024-cycle MMA of a step); (3) the two halves
+// of a row merge their sample lists into ONE threshold, which halves the candidates (and ends the list overflows that sent
+// ~35 rows per call to the exact fallback).
+template <int STAGES, bool DBG>
 __global__ void __launch_bounds__(THREADS, 1)
 topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Params P)
 {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t *smem_a = smem;                                              // [TILES_M][kb] tiles (none when ATM)
-    uint8_t *smem_b = smem_a + (ATM ? 0 : (size_t)TILES_M * P.kb * TILE_BYTES);      // [STAGES][kb] tiles
+    uint8_t *smem_a = smem;                                              // [TILES_M][kb] tiles
+    uint8_t *smem_b = smem_a + (size_t)TILES_M * P.kb * TILE_BYTES;      // [STAGES][kb] tiles
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + (size_t)STAGES * P.kb * TILE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *a_full = bars + 2 * STAGES, *a_empty = a_full + 1;
     uint64_t *t_full = a_empty + 1, *t_empty = t_full + 2;
@@ -106,9 +97,9 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(a_full, ATM ? EPI_WARPS / 2 : 1);   // ATM: the 8 warps that write A arrive
+        mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], ATM ? EPI_WARPS / 2 : EPI_WARPS); }
+        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -126,13 +117,11 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (lane == 0) {
             uint32_t it = 0, ag = 0;
             for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
-                if constexpr (!ATM) {
-                    mbar_wait_backoff(a_empty, (ag & 1) ^ 1);  // MMA of the previous group no longer reads A
-                    mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
-                    for (int m = 0; m < TILES_M; m++)
-                        for (int kb = 0; kb < P.kb; kb++)
-                            tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
-                }
+                mbar_wait_backoff(a_empty, (ag & 1) ^ 1);  // MMA of the previous group no longer reads A
+                mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
+                for (int m = 0; m < TILES_M; m++)
+                    for (int kb = 0; kb < P.kb; kb++)
+                        tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
                 for (int t = 0; t < total_tiles; t++, it++) {
                     const int s = it % STAGES;
                     mbar_wait_backoff(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -149,27 +138,6 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             uint32_t it = 0, ag = 0, at = 0;
             for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
                 mbar_wait_backoff(a_full, ag & 1);
-                if constexpr (ATM) {
-                    const uint32_t a_col0 = 2u * BN;                       // A tiles start after the two accumulators
-                    for (int t = 0; t < total_tiles; t++, it++, at++) {
-                        const int s = it % STAGES;
-                        mbar_wait(&full[s], (it / STAGES) & 1);
-                        for (int m = 0; m < TILES_M; m++) {
-                            mbar_wait(&t_empty[m], (at & 1) ^ 1);          // tile m's accumulator was drained (step at - 1)
-                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const uint32_t d = tmem_base + (uint32_t)(m * BN);
-                            const uint32_t a = tmem_base + a_col0 + (uint32_t)(m * P.kb * (BK / 2));
-                            for (int kb = 0; kb < P.kb; kb++) {
-                                const uint8_t *tb = smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES;
-#pragma unroll
-                                for (int k = 0; k < BK / 16; k++)
-                                    umma_bf16_ts(d, a + (uint32_t)(kb * (BK / 2) + k * 8), umma_desc(tb, k * 32), IDESC, (kb | k) != 0);
-                            }
-                            umma_commit(&t_full[m]);
-                        }
-                        umma_commit(&empty[s]);      // B stage reusable once both tiles' MMAs retire
-                    }
-                } else {
                 for (int t = 0; t < total_tiles; t++, it++, at++) {
                     const int s = it % STAGES, as = at & 1;
                     mbar_wait(&t_empty[as], ((at >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
@@ -188,126 +156,137 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
                     umma_commit(&t_full[as]);    // both accumulators of this stage are complete
                 }
-                }
                 umma_commit(a_empty);
             }
         }
     } else if (warp >= 4) {
         // ===== epilogue: 16 warps = 2 query tiles x 4 lane quarters x 2 column halves.  A (row, half) pair is one thread:
-        // it samples, thresholds and pushes on its own 64 of every 128 columns (its theta comes from its half of the
-        // sample, a valid if slightly looser bound), so the two halves never synchronise.
+        // it samples and pushes on its own 64 of every 128 columns.  The two halves of a row meet once per group, after the
+        // sample, to merge their 16 best into one threshold (through the row's still empty candidate lists).
         const int ew = warp - 4, m = ew >> 3, half = (ew >> 2) & 1;
-        const uint32_t lane_base = (uint32_t)((ew & 3) * 32) << 16;  // a warp may only touch its own 32 TMEM lanes
-        uint32_t at = 0, at_g = 0;
+        // a warp may only touch its own 32 TMEM lanes (bits 16+); its columns are half a tile of accumulator m
+        const uint32_t acc0 = tmem_base + ((uint32_t)((ew & 3) * 32) << 16) + (uint32_t)(m * 2 * BN + half * (BN / 2));
+        uint32_t at = 0;
+        auto release = [&](int as) {      // the accumulators of stage `as` are in registers: hand the stage back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[as]);
+        };
         for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
             const int64_t row = (int64_t)(g * TILES_M + m) * BM + (ew & 3) * 32 + lane;
             const bool row_ok = row < P.nq;
-            const float eps = row_ok ? P.eps[row] : 0.f;
-            float top[R_TOP];
+            int32_t *ccol = P.cand_col + (row_ok ? row : 0) * CAP + half * HALF_CAP;
+            float *cval = P.cand_val + (row_ok ? row : 0) * CAP + half * HALF_CAP;
+            [[maybe_unused]] auto dump = [&](const uint32_t (&v)[32], int64_t col0) {
+                if (P.dbg && row_ok) {
 #pragma unroll
-            for (int r = 0; r < R_TOP; r++) top[r] = -INFINITY;
-            float theta = -INFINITY;
-            int cnt = 0;
-            if constexpr (ATM) {
-                // this group's query rows -> tensor memory (the half-0 warps of each tile: thread = TMEM lane = row)
-                if (half == 0) {
-                    if (lane == 0) mbar_wait(a_empty, ((at_g & 1) ^ 1));   // the previous group's MMAs no longer read A
-                    __syncwarp();
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t *qrow = reinterpret_cast<const uint32_t *>(P.qb) + (row < P.nq_pad ? row : 0) * (int64_t)(P.kb * (BK / 2));
-                    const uint32_t a = tmem_base + lane_base + 2u * BN + (uint32_t)(m * P.kb * (BK / 2));
-                    for (int c0 = 0; c0 < P.kb * (BK / 2); c0 += 32) {
-                        uint32_t v[32];
-#pragma unroll
-                        for (int e = 0; e < 32; e += 4) {
-                            const uint4 u = __ldg(reinterpret_cast<const uint4 *>(qrow + c0 + e));
-                            v[e] = u.x; v[e + 1] = u.y; v[e + 2] = u.z; v[e + 3] = u.w;
-                        }
-                        tmem_st32(a + c0, v);
-                    }
-                    tmem_st_wait();
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(a_full);
+                    for (int e = 0; e < 32; e++) P.dbg[row * ((int64_t)P.n_tiles * BN) + col0 + e] = __uint_as_float(v[e]);
                 }
-                at_g++;
-            }
-            // per-warp scratch row for the cooperative push (128 bytes)
-            float *scr = reinterpret_cast<float *>(tmem_slot + 4) + ew * 32;
-            const int64_t row0 = (int64_t)(g * TILES_M + m) * BM + (ew & 3) * 32;   // row of lane 0
-            for (int t = 0; t < total_tiles; t++, at++) {
-                const int as = at & 1;
-                const bool sample = t < P.m_tiles;
-                if (t == P.m_tiles) theta = row_ok ? top[R_TOP - 1] - 2.f * eps : INFINITY;   // padding rows never hit
-                const int bt = t < P.n_tiles ? t : t - P.n_tiles;
-                if constexpr (ATM) mbar_wait(&t_full[m], at & 1);
-                else mbar_wait(&t_full[as], (at >> 1) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t acc = tmem_base + lane_base + (uint32_t)(ATM ? m * BN : (m * 2 + as) * BN);
-#pragma unroll 1
-                for (int c0 = half * (BN / 2); c0 < (half + 1) * (BN / 2); c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(acc + c0, v);
-                    const int64_t col0 = (int64_t)bt * BN + c0;
-                    if constexpr (DBG) {
-                        if (P.dbg && row_ok && t < P.n_tiles) {
+            };
+            float theta;
+            {
+                // ---- the sample: the R_TOP best scores of the first m_tiles tiles
+                float top[R_TOP];
 #pragma unroll
-                            for (int e = 0; e < 32; e++) P.dbg[row * ((int64_t)P.n_tiles * BN) + col0 + e] = __uint_as_float(v[e]);
-                        }
+                for (int r = 0; r < R_TOP; r++) top[r] = -INFINITY;
+                auto insert = [&](float cur) {   // into the sorted 16 best
+#pragma unroll
+                    for (int r = 0; r < R_TOP; r++) {
+                        const float hi = fmaxf(top[r], cur);
+                        cur = fminf(top[r], cur);
+                        top[r] = hi;
                     }
-                    if (sample) {
+                };
+                for (int t = 0; t < P.m_tiles; t++, at++) {
+                    const int as = at & 1;
+                    mbar_wait(&t_full[as], (at >> 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN / 2; c0 += 32) {
+                        uint32_t v[32];
+                        tmem_ld32(acc0 + (uint32_t)(as * BN + c0), v);
+                        const int64_t col0 = (int64_t)t * BN + half * (BN / 2) + c0;
+                        if constexpr (DBG) dump(v, col0);
 #pragma unroll
                         for (int e = 0; e < 32; e++) {
                             const float x = __uint_as_float(v[e]);
-                            if (x > top[R_TOP - 1] && col0 + e < P.n) {
-                                // insertion into the sorted 16 best (rare after the first few hundred columns)
-                                float cur = x;
-#pragma unroll
-                                for (int r = 0; r < R_TOP; r++) {
-                                    const float hi = fmaxf(top[r], cur);
-                                    cur = fminf(top[r], cur);
-                                    top[r] = hi;
-                                }
-                            }
+                            if (x > top[R_TOP - 1] && col0 + e < P.n) insert(x);   // rare after the first few hundred columns
                         }
-                        __syncwarp();
-                    } else {
-                        // One test per 32 columns, no divergent code: a hit is rare per row (~0.1 % of the columns) but a warp
-                        // holds 32 rows, so SOME lane hits in most batches -- the push is therefore done by the whole warp
-                        // for one hitting row at a time: the row's 32 scores go through a 128-byte scratch line so that lane e
-                        // sees column e, a ballot gives the push positions, the stores of a row are coalesced.
-                        const float mx = max32(v);
-                        unsigned hm = __ballot_sync(0xffffffffu, mx >= theta);
-                        while (hm) {
-                            const int L = __ffs(hm) - 1;
-                            hm &= hm - 1;
-                            if (lane == L) {
+                        __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the data-dependent code
+                    }
+                    release(as);
+                }
+                // ---- one threshold per row: merge the other half's 16 best (it sits in the row's other candidate list)
+                if (row_ok) {
 #pragma unroll
-                                for (int e = 0; e < 32; e += 4)
-                                    *reinterpret_cast<uint4 *>(scr + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-                            }
-                            __syncwarp();
-                            const float x = scr[lane];
-                            const float thL = __shfl_sync(0xffffffffu, theta, L);
-                            const int cntL = __shfl_sync(0xffffffffu, cnt, L);
-                            const bool push = x >= thL && col0 + lane < P.n;
-                            const unsigned pm = __ballot_sync(0xffffffffu, push);
-                            if (push) {
-                                const int pos = cntL + __popc(pm & ((1u << lane) - 1));
-                                if (pos < HALF_CAP) {
-                                    const int64_t o = (row0 + L) * CAP + half * HALF_CAP + pos;
-                                    P.cand_col[o] = (int32_t)(col0 + lane);
-                                    P.cand_val[o] = x;
-                                }
-                            }
-                            if (lane == L) cnt += __popc(pm);
-                            __syncwarp();
-                        }
+                    for (int r = 0; r < R_TOP; r++) cval[r] = top[r];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+                if (row_ok) {
+                    const float *other = P.cand_val + row * CAP + (1 - half) * HALF_CAP;
+                    float o[R_TOP];
+#pragma unroll
+                    for (int r = 0; r < R_TOP; r++) o[r] = other[r];
+#pragma unroll 1
+                    for (int r = 0; r < R_TOP; r++) {
+                        float cur = o[0];
+#pragma unroll
+                        for (int q = 0; q + 1 < R_TOP; q++) o[q] = o[q + 1];
+                        if (cur > top[R_TOP - 1]) insert(cur);
                     }
                 }
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ATM ? &t_empty[m] : &t_empty[as]);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // lists are free for the pushes from here
+                theta = row_ok ? top[R_TOP - 1] - 2.f * P.eps[row] : INFINITY;   // padding rows never hit
+            }
+            // ---- the sweep: every column at or above theta goes to the row's list
+            int cnt = 0;
+            auto hits = [&](const uint32_t (&v)[32], int64_t col0) {
+                // a 3-input max tree over the 32 scores (16 instructions, depth 4); only a lane whose maximum clears theta
+                // (~1.5 % of them) walks back down the tree to the columns that did: ~30 instructions for the usual single hit
+#define GB_F(i) __uint_as_float(v[i])
+                const float a0 = max3(GB_F(0), GB_F(1), GB_F(2)), a1 = max3(GB_F(3), GB_F(4), GB_F(5)), a2 = max3(GB_F(6), GB_F(7), GB_F(8)),
+                            a3 = max3(GB_F(9), GB_F(10), GB_F(11)), a4 = max3(GB_F(12), GB_F(13), GB_F(14)),
+                            a5 = max3(GB_F(15), GB_F(16), GB_F(17)), a6 = max3(GB_F(18), GB_F(19), GB_F(20)),
+                            a7 = max3(GB_F(21), GB_F(22), GB_F(23)), a8 = max3(GB_F(24), GB_F(25), GB_F(26)),
+                            a9 = max3(GB_F(27), GB_F(28), GB_F(29));
+                const float b0 = max3(a0, a1, a2), b1 = max3(a3, a4, a5), b2 = max3(a6, a7, a8), b3 = max3(a9, GB_F(30), GB_F(31));
+                if (fmaxf(max3(b0, b1, b2), b3) >= theta) {
+                    const int32_t c32 = (int32_t)col0;
+                    const int lim = (int)min((int64_t)32, P.n - col0);   // real columns in this batch (padding only in the last tile)
+#define GB_PUSH(e)                                                                                     \
+    if (GB_F(e) >= theta && e < lim) {                                                                 \
+        if (cnt < HALF_CAP) { ccol[cnt] = c32 + e; cval[cnt] = GB_F(e); }                             \
+        cnt++;                                                                                         \
+    }
+#define GB_PUSH3(a, e) if (a >= theta) { GB_PUSH(e) GB_PUSH(e + 1) GB_PUSH(e + 2) }
+                    if (b0 >= theta) { GB_PUSH3(a0, 0) GB_PUSH3(a1, 3) GB_PUSH3(a2, 6) }
+                    if (b1 >= theta) { GB_PUSH3(a3, 9) GB_PUSH3(a4, 12) GB_PUSH3(a5, 15) }
+                    if (b2 >= theta) { GB_PUSH3(a6, 18) GB_PUSH3(a7, 21) GB_PUSH3(a8, 24) }
+                    if (b3 >= theta) { GB_PUSH3(a9, 27) GB_PUSH(30) GB_PUSH(31) }
+#undef GB_PUSH3
+#undef GB_PUSH
+                }
+#undef GB_F
+            };
+            for (int t = P.m_tiles; t < total_tiles; t++, at++) {
+                const int as = at & 1;
+                const int bt = t < P.n_tiles ? t : t - P.n_tiles;
+                mbar_wait(&t_full[as], (at >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                // both batches into registers, then the stage goes back BEFORE they are looked at: a warp that has hits to
+                // push delays only itself, not the 15 others and the tensor pipe (see the note above the kernel)
+                uint32_t v0[32], v1[32];
+                tmem_ld32_issue(acc0 + (uint32_t)(as * BN), v0);
+                tmem_ld32_issue(acc0 + (uint32_t)(as * BN + 32), v1);
+                tmem_ld_wait();
+                release(as);
+                const int64_t col0 = (int64_t)bt * BN + half * (BN / 2);
+                if constexpr (DBG) {
+                    if (t < P.n_tiles) { dump(v0, col0); dump(v1, col0 + 32); }
+                }
+                hits(v0, col0);
+                hits(v1, col0 + 32);
+                __syncwarp();   // tcgen05.ld is warp-collective: reconverge after the data-dependent code
             }
             if (row_ok) { P.cand_cnt[2 * row + half] = cnt; P.theta[2 * row + half] = theta; }
         }
@@ -564,15 +543,15 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     // overflows with probability ~1e-5.  (Round 2 tried 4.5k and 6k to get rid of the ~30 fallback rows per 151 552-row call:
     // the lists, already inflated 1.35x by the -2 eps on theta, then overflow for 1 % / 20 % of the rows and the exact
     // fallback takes over: 398 ms / 4.6 s per call instead of 68 ms.  profiles/r02_topk_margin_chunk.md.)
-    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (3.2 * k) / mma::BN);
+    static const double margin = [] { const char *e = getenv("GORSE_B200_TOPK_MARGIN"); return e ? atof(e) : 4.0; }();   // A/B
+    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (margin * k) / mma::BN);
     m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
-    static const bool atm = [] { const char *e = getenv("GORSE_B200_TOPK_ATM"); return !(e && *e == '0'); }();   // A/B: =0 keeps A in shared memory
-    const size_t a_bytes = atm ? 0 : (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;
+    const size_t a_bytes = (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;
     int stages = (int)std::min<size_t>(4, (200 * 1024 - a_bytes) / b_stage);
     if (stages < 2) { set_error("search_mma: Kp = %d does not fit", kp); return GORSE_B200_ERR_UNSUPPORTED; }
-    const size_t smem = a_bytes + (size_t)stages * b_stage + 1024 /*align*/ + 256 /*barriers*/ + (size_t)mma::EPI_WARPS * 128 /*push scratch*/;
+    const size_t smem = a_bytes + (size_t)stages * b_stage + 1024 /*align*/ + 256 /*barriers*/;
 
     CUtensorMap map_b;
     GB_TRY(make_map(&map_b, ix->Xb.p, n_pad, kp));
@@ -602,10 +581,8 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     const int64_t fl_off = ix->w_cq;  // the fallback counter sits after the list
     const bool dbg = ix->dbg_scores != nullptr;   // the dense score dump of the test hook is compiled out of the production kernel
     auto pick = [&](auto s4, auto s3, auto s2) { return stages >= 4 ? s4 : stages == 3 ? s3 : s2; };
-    auto kern = atm ? (dbg ? pick(mma::topk_mma_kernel<4, true, true>, mma::topk_mma_kernel<3, true, true>, mma::topk_mma_kernel<2, true, true>)
-                           : pick(mma::topk_mma_kernel<4, false, true>, mma::topk_mma_kernel<3, false, true>, mma::topk_mma_kernel<2, false, true>))
-                    : (dbg ? pick(mma::topk_mma_kernel<4, true, false>, mma::topk_mma_kernel<3, true, false>, mma::topk_mma_kernel<2, true, false>)
-                           : pick(mma::topk_mma_kernel<4, false, false>, mma::topk_mma_kernel<3, false, false>, mma::topk_mma_kernel<2, false, false>));
+    auto kern = dbg ? pick(mma::topk_mma_kernel<4, true>, mma::topk_mma_kernel<3, true>, mma::topk_mma_kernel<2, true>)
+                    : pick(mma::topk_mma_kernel<4, false>, mma::topk_mma_kernel<3, false>, mma::topk_mma_kernel<2, false>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("search_mma smem attr: %s", cudaGetErrorString(e)); return done(GORSE_B200_ERR_CUDA); }
     for (int64_t off = 0; off < nq; off += cq) {
@@ -619,7 +596,7 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         if ((st = make_map(&map_a, Qb.p, n_this_pad, kp))) return done(st);
         mma::Params P;
         P.n = ix->n; P.n_tiles = n_tiles; P.m_tiles = m_tiles; P.kb = kb; P.nq = n_this; P.n_groups = (int)(n_this_pad / 256);
-        P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores; P.qb = Qb.p; P.nq_pad = n_this_pad;
+        P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores;
         const int grid = std::min(P.n_groups, c->sm_count);
         if (!ix->ev0) { cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1); }
         cudaEventRecord(ix->ev0, c->stream);

@@ -52,12 +52,13 @@ def test_stage1_scores_match_bf16_matmul(gb, ctx, metric, d):
     want = Xb[100:400] @ Xb.T
     if metric == "euclid":
         want = want - 0.5 * (X.astype(np.float64) ** 2).sum(1)[None, :]
-    assert np.abs(got - want).max() < 2e-3, np.abs(got - want).max()
-    # and the error bound the filter relies on: |stage-1 score - exact| <= eps = 1.02 * 2^-8 * |q| * max|x|
+    acc_err = 0.0
+    assert np.abs(got - want).max() < 2e-3 + acc_err, np.abs(got - want).max()
+    # and the error bound the filter relies on: |stage-1 score - exact| <= eps = (1.02 * 2^-8 [+ n_mma * 2^-11]) * |q| * max|x|
     exact = X[100:400].astype(np.float64) @ X.astype(np.float64).T
     if metric == "euclid":
         exact = exact - 0.5 * (X.astype(np.float64) ** 2).sum(1)[None, :]
-    assert np.abs(got - exact).max() <= 1.02 / 256
+    assert np.abs(got - exact).max() <= 1.02 / 256 + acc_err
 
 
 @pytest.mark.parametrize("metric,d,k", [("negdot", 128, 100), ("euclid", 64, 100), ("negdot", 64, 10), ("euclid", 128, 37)])
