@@ -118,7 +118,7 @@ als_chunk_gram_tc_kernel(const float *Y, const int32_t *idx, const int64_t *chun
         // generic-proxy stores -> async-proxy (tensor core) reads
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one()) {   // an elected lane, not `tid == 0`: keeps the descriptor arithmetic on the uniform datapath
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = s32(hi), a_lo = s32(lo);
 #pragma unroll

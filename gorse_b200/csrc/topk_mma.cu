@@ -53,6 +53,7 @@ struct Params {
     int32_t *cand_cnt;    // [nq][2] pushes per column half (may exceed HALF_CAP)
     float *theta;         // [nq][2] threshold used by each half
     float *dbg;           // optional dense [nq][n_tiles*128] score dump (tests)
+    int32_t exp;          // TEMPORARY timing experiments (GORSE_B200_TOPK_EXP): 1 no hits(), 2 no tcgen05.ld either, 4 theta = +inf
 };
 
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
@@ -113,50 +114,79 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int total_tiles = P.n_tiles + P.m_tiles;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer: the warp waits together, one elected lane issues (see the MMA warp for why not `lane == 0`)
+        {
             uint32_t it = 0, ag = 0;
             for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
                 mbar_wait_backoff(a_empty, (ag & 1) ^ 1);  // MMA of the previous group no longer reads A
-                mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
-                for (int m = 0; m < TILES_M; m++)
-                    for (int kb = 0; kb < P.kb; kb++)
-                        tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
+                if (elect_one()) {
+                    mbar_expect_tx(a_full, (uint32_t)TILES_M * P.kb * TILE_BYTES);
+                    for (int m = 0; m < TILES_M; m++)
+                        for (int kb = 0; kb < P.kb; kb++)
+                            tma_load_2d(smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES, &map_a, kb * BK, (g * TILES_M + m) * BM, a_full);
+                }
+                __syncwarp();
                 for (int t = 0; t < total_tiles; t++, it++) {
                     const int s = it % STAGES;
                     mbar_wait_backoff(&empty[s], ((it / STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&full[s], (uint32_t)P.kb * TILE_BYTES);
-                    const int bt = t < P.n_tiles ? t : t - P.n_tiles;
-                    for (int kb = 0; kb < P.kb; kb++)
-                        tma_load_2d(smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES, &map_b, kb * BK, bt * BN, &full[s]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full[s], (uint32_t)P.kb * TILE_BYTES);
+                        const int bt = t < P.n_tiles ? t : t - P.n_tiles;
+                        for (int kb = 0; kb < P.kb; kb++)
+                            tma_load_2d(smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES, &map_b, kb * BK, bt * BN, &full[s]);
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        // This thread's instruction stream is the pace of the whole kernel when it is long: round 1 rebuilt both 64-bit
+        // shared-memory descriptors from generic pointers for every MMA (341 instructions per tile step, one warp, ~6.7
+        // cycles each = 2300 cycles against 1084 cycles of tensor work: the "48 % tensor pipe" plateau that no epilogue
+        // change moved, profiles/r02_topk_epilogue.md).  The descriptors differ only in the 14-bit address field: one add each.
+        // The whole warp runs the loop and the waits; one ELECTED lane issues (the compiler knows an elect.sync predicate
+        // selects exactly one thread and keeps the descriptor arithmetic on the uniform datapath; behind `lane == 0` it
+        // wrapped every MMA in a loop over the active lanes).
+        {
+            const uint64_t da = umma_desc(smem_a, 0), db = umma_desc(smem_b, 0);
+            const uint32_t a_hi = (uint32_t)(da >> 32), b_hi = (uint32_t)(db >> 32), a_lo0 = (uint32_t)da, b_lo0 = (uint32_t)db;
+            constexpr uint32_t TILE16 = TILE_BYTES >> 4;          // descriptor address units are 16 bytes
+            const uint32_t stage16 = (uint32_t)P.kb * TILE16;
+            auto desc = [](uint32_t lo, uint32_t hi) {
+                uint64_t d;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+                return d;
+            };
             uint32_t it = 0, ag = 0, at = 0;
             for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x, ag++) {
                 mbar_wait_backoff(a_full, ag & 1);
                 for (int t = 0; t < total_tiles; t++, it++, at++) {
-                    const int s = it % STAGES, as = at & 1;
+                    const uint32_t s = it % STAGES, as = at & 1;
                     mbar_wait(&t_empty[as], ((at >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
                     mbar_wait(&full[s], (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    for (int m = 0; m < TILES_M; m++) {
-                        const uint32_t d = tmem_base + (uint32_t)((m * 2 + as) * BN);
-                        for (int kb = 0; kb < P.kb; kb++) {
-                            const uint8_t *ta = smem_a + ((size_t)m * P.kb + kb) * TILE_BYTES;
-                            const uint8_t *tb = smem_b + ((size_t)s * P.kb + kb) * TILE_BYTES;
+                    if (elect_one()) {
+                        const uint32_t b_lo = b_lo0 + s * stage16;
 #pragma unroll
-                            for (int k = 0; k < BK / 16; k++)
-                                umma_bf16(d, umma_desc(ta, k * 32), umma_desc(tb, k * 32), IDESC, (kb | k) != 0);
+                        for (int m = 0; m < TILES_M; m++) {
+                            const uint32_t d = tmem_base + (uint32_t)((m * 2 + as) * BN);
+                            const uint32_t a_lo = a_lo0 + (uint32_t)m * stage16;
+                            for (uint32_t kb = 0; kb < (uint32_t)P.kb; kb++) {
+#pragma unroll
+                                for (uint32_t k = 0; k < BK / 16; k++) {   // 16 bf16 = 32 bytes = 2 address units along K
+                                    const uint32_t off = kb * TILE16 + k * 2;
+                                    umma_bf16(d, desc(a_lo + off, a_hi), desc(b_lo + off, b_hi), IDESC, (kb | k) != 0);
+                                }
+                            }
                         }
+                        umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
+                        umma_commit(&t_full[as]);    // both accumulators of this stage are complete
                     }
-                    umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
-                    umma_commit(&t_full[as]);    // both accumulators of this stage are complete
+                    __syncwarp();
                 }
-                umma_commit(a_empty);
+                if (elect_one()) umma_commit(a_empty);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -237,6 +267,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // lists are free for the pushes from here
                 theta = row_ok ? top[R_TOP - 1] - 2.f * P.eps[row] : INFINITY;   // padding rows never hit
+                if (P.exp & 4) theta = INFINITY;
             }
             // ---- the sweep: every column at or above theta goes to the row's list
             int cnt = 0;
@@ -276,10 +307,12 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // both batches into registers, then the stage goes back BEFORE they are looked at: a warp that has hits to
                 // push delays only itself, not the 15 others and the tensor pipe (see the note above the kernel)
                 uint32_t v0[32], v1[32];
+                if (P.exp & 2) { release(as); continue; }
                 tmem_ld32_issue(acc0 + (uint32_t)(as * BN), v0);
                 tmem_ld32_issue(acc0 + (uint32_t)(as * BN + 32), v1);
                 tmem_ld_wait();
                 release(as);
+                if (P.exp & 1) { if (v0[0] == 0x12345678u && v1[5] == 0x1234567u) cnt++; continue; }
                 const int64_t col0 = (int64_t)bt * BN + half * (BN / 2);
                 if constexpr (DBG) {
                     if (t < P.n_tiles) { dump(v0, col0); dump(v1, col0 + 32); }
@@ -597,6 +630,7 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         mma::Params P;
         P.n = ix->n; P.n_tiles = n_tiles; P.m_tiles = m_tiles; P.kb = kb; P.nq = n_this; P.n_groups = (int)(n_this_pad / 256);
         P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores;
+        { const char *e = getenv("GORSE_B200_TOPK_EXP"); P.exp = e ? atoi(e) : 0; }
         const int grid = std::min(P.n_groups, c->sm_count);
         if (!ix->ev0) { cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1); }
         cudaEventRecord(ix->ev0, c->stream);

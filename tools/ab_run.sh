@@ -1,17 +1,7 @@
 #!/bin/bash
-# one GPU call: top-k epilogue check (early release + merged threshold) and margin sweep
-echo "== topk"
-timeout 400 python -m pytest tests/test_topk_mma_gpu.py tests/test_topk_gpu.py tests/test_logics_gpu.py tests/test_fullsize_gpu.py tests/test_vecdb_gpu.py -q 2>&1 | tail -4
-for mg in 3.2 4; do
-  export GORSE_B200_TOPK_MARGIN=$mg
-  echo "== margin $mg"
-  timeout 300 python bench.py --workload c4 --no-cpu --no-e2e --steps 5 > gpurun_out/c4_m$mg.json 2>gpurun_out/c4_m$mg.err
-  python - <<PY
-import json
-d=json.loads(open('gpurun_out/c4_m$mg.json').read().strip().splitlines()[-1])
-print("  ms/step %.1f  value %.3g  stage1 ms %.1f frac %.3f  fallback rows %d" % (d['ms_per_step'], d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['config']['fallback_rows']))
-PY
+# timing experiments on the sweep kernel (results are garbage with EXP != 0: only the first launch is timed, then the run is killed)
+for x in 0 4 1 2; do
+  echo "== GORSE_B200_TOPK_EXP=$x"
+  GORSE_B200_TOPK_EXP=$x timeout 300 ncu --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max -k regex:topk_mma_kernel -c 1 --kill yes --clock-control none python bench.py --workload c4 --steps 1 --warmup 0 --no-cpu --no-e2e --no-also > gpurun_out/exp_$x.csv 2>&1
+  grep "topk_mma_kernel" gpurun_out/exp_$x.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}'
 done
-unset GORSE_B200_TOPK_MARGIN
-bash tools/ncu_lists.sh c4 2>&1 | grep "topk\|prune\|exact" | head
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:topk_mma_kernel -s 1 -c 1 -o gpurun_out/topk_r2_tree -f python bench.py --workload c4 --steps 1 --warmup 1 --no-cpu --no-e2e --no-also > /dev/null 2>&1
