@@ -6,10 +6,12 @@
 // Roofline class: HBM bandwidth (one gather of the opposite table's rows per feedback + own row + one
 // Gram pass): B_epoch = 2|R|(4d+4) + 3(U+I)4d bytes.
 //
-// Row updates come in three forms, chosen per row by its length (prepare_als):
-//   * als_rows_group_kernel (d % 32 == 0, d <= 128, rows up to 96 entries): a group of 8/16/32 lanes per row, g = S x
-//     kept current in registers, B coordinates resolved per shuffle butterfly (see the comment at the kernel);
-//   * Gram form for longer rows (als_chunk_gram_kernel + als_solve_kernel): one Gauss-Seidel sweep on A x = h;
+// Row updates come in four forms, chosen per row by its length (prepare_als):
+//   * als_thread_kernel (als_thread.cu; d % 32 == 0, d <= 128, rows up to 4 entries): one thread per row;
+//   * als_rows_group_blocked_kernel (same d, rows up to 96 entries): a group of 8/16/32 lanes per row, g = S x kept
+//     current in registers, the gathered rows staged one block of G coordinates at a time;
+//   * Gram form for longer rows (tcgen05 chunk Grams at d = 128, als_gram_tc.cu, else als_chunk_gram_kernel; then
+//     als_solve_kernel): one Gauss-Seidel sweep on A x = h;
 //   * als_rows_kernel, one warp per row with the reference's loop structure, for the remaining shapes (d not a
 //     multiple of 32 or > 128).  The gathered rows Y[R_x] are staged once in shared memory ([n][d+1], the +1 makes the
 //     per-f column walk conflict-free), the running predictions live in registers.
@@ -271,12 +273,6 @@ als_rows_kernel(float *X, const float *Y, int d, int32_t x_lo, int32_t y_lo, con
 // shared memory as [t][d+1] (conflict-free both along a row and down a column) next to one copy of S per CTA.
 // Differences from the reference are reassociation (lane-parallel sums, incremental g) and one reciprocal-multiply
 // instead of a divide: observed ~1e-6 relative, budget 1e-4.
-// floats of shared memory per lane group; padded so that the groups of one warp start G banks apart
-__host__ __device__ constexpr int group_stage_floats(int G, int E, int DP)
-{
-    return G * E * DP + ((G < 32 && (G * E * DP) % 32 == 0) ? G : 0);
-}
-
 template <int G>
 __device__ __forceinline__ float group_sum(float v)
 {
@@ -285,158 +281,9 @@ __device__ __forceinline__ float group_sum(float v)
     return v;
 }
 
-template <int G, int E, int KPL, int B>
-__global__ void __launch_bounds__(256)
-als_rows_group_kernel(float *X, const float *Y, const int64_t *off, const int32_t *idx, const float *S, float reg, float w,
-                      const int32_t *row_ids, int32_t n_rows)
-{
-    constexpr int D = G * KPL, DP = D + 1, NG = 32 / G, D4 = D / 4;
-    extern __shared__ float smem[];
-    float *Ss = smem;                                   // [D][D]
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int grp = lane / G, j = lane % G;
-    float *ys = smem + D * D + (size_t)(wid * NG + grp) * group_stage_floats(G, E, DP);
-    for (int e = threadIdx.x; e < D * D; e += blockDim.x) Ss[e] = S[e];
-    __syncthreads();
-    const float omw = 1.0f - w;
-    const int32_t stride = gridDim.x * nw * NG;
-    for (int32_t base = (blockIdx.x * nw + wid) * NG; base < n_rows; base += stride) {   // warp-uniform trip count
-        const int32_t slot = base + grp;
-        const bool act = slot < n_rows;
-        int32_t r = 0;
-        int n = 0;
-        int64_t o = 0;
-        if (act) { r = row_ids[slot]; o = off[r]; n = (int)(off[r + 1] - o); }
-        // stage the gathered rows: the group's lanes walk the n*D/4 float4 pieces
-#pragma unroll 4
-        for (int c = j; c < n * D4; c += G) {
-            const int t = c / D4, q = c - t * D4;
-            const float4 v = __ldg(reinterpret_cast<const float4 *>(Y + (int64_t)idx[o + t] * D) + q);
-            float *dst = ys + t * DP + 4 * q;
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-        }
-        float x[KPL], g[KPL], h[KPL], cw[KPL], inv[KPL], pred[E];
-#pragma unroll
-        for (int i = 0; i < KPL; i++) {
-            x[i] = act ? X[(int64_t)r * D + i * G + j] : 0.f;
-            g[i] = 0.f; h[i] = 0.f; cw[i] = 0.f;
-        }
-#pragma unroll
-        for (int e = 0; e < E; e++) pred[e] = 0.f;
-        __syncwarp();
-        // pred_t = x . y_t (:661-663), h, c in one pass over the staged rows
-        const int nmax = __reduce_max_sync(0xffffffffu, n);
-#pragma unroll
-        for (int e = 0; e < E; e++) {
-#pragma unroll 1
-            for (int tt = 0; tt < G; tt++) {
-                const int t = e * G + tt;
-                if (t >= nmax) break;                    // warp-uniform
-                float part = 0.f;
-                if (t < n) {
-#pragma unroll
-                    for (int i = 0; i < KPL; i++) {
-                        const float y = ys[t * DP + i * G + j];
-                        part = fmaf(x[i], y, part);
-                        h[i] += y;
-                        cw[i] = fmaf(y, y, cw[i]);
-                    }
-                }
-                part = group_sum<G>(part);
-                if (tt == j) pred[e] = part;
-            }
-        }
-        // g = S x (S symmetric: row m is column m), cw = (1-w) c + w S_kk, inv = 1 / (cw + reg)
-#pragma unroll
-        for (int mi = 0; mi < KPL; mi++) {
-#pragma unroll 1
-            for (int mj = 0; mj < G; mj++) {
-                const float xm = __shfl_sync(0xffffffffu, x[mi], mj, G);
-                const float *srow = Ss + (mi * G + mj) * D + j;
-#pragma unroll
-                for (int i = 0; i < KPL; i++) g[i] = fmaf(xm, srow[i * G], g[i]);
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < KPL; i++) {
-            const int k = i * G + j;
-            cw[i] = omw * cw[i] + w * Ss[k * D + k];
-            inv[i] = 1.0f / (cw[i] + reg);
-        }
-        // the sequential sweep over f = fi*G + jo, B coordinates at a time: the B reductions z_b = sum_t pred_t y_tb and
-        // the B(B-1)/2 in-block products M_ab = sum_t y_ta y_tb run as ONE interleaved butterfly, then the coordinates
-        // are resolved in order with z_b += delta_a * M_ab  (pred_t moves by delta_a * y_ta, hence z_b by delta_a * M_ab):
-        // same arithmetic as one coordinate at a time up to rounding, a B-fold shorter dependent chain of shuffles.
-        constexpr int NV = B + B * (B - 1) / 2;
-#pragma unroll
-        for (int fi = 0; fi < KPL; fi++) {
-#pragma unroll 1
-            for (int jb = 0; jb < G / B; jb++) {
-                const int f0 = fi * G + jb * B;
-                float ye[E][B], red[NV], dls[B];
-#pragma unroll
-                for (int e = 0; e < E; e++) {
-                    const int t = j + e * G;
-#pragma unroll
-                    for (int a = 0; a < B; a++) ye[e][a] = t < n ? ys[t * DP + f0 + a] : 0.f;
-                }
-#pragma unroll
-                for (int a = 0; a < B; a++) {
-                    float v = 0.f;
-#pragma unroll
-                    for (int e = 0; e < E; e++) v = fmaf(pred[e], ye[e][a], v);
-                    red[a] = v;
-                }
-                {
-                    int q = B;
-#pragma unroll
-                    for (int a = 0; a < B; a++)
-#pragma unroll
-                        for (int b2 = a + 1; b2 < B; b2++) {
-                            float v = 0.f;
-#pragma unroll
-                            for (int e = 0; e < E; e++) v = fmaf(ye[e][a], ye[e][b2], v);
-                            red[q++] = v;
-                        }
-                }
-#pragma unroll
-                for (int o = G / 2; o; o >>= 1)
-#pragma unroll
-                    for (int v = 0; v < NV; v++) red[v] += __shfl_xor_sync(0xffffffffu, red[v], o);
-                {
-                    int q = B;
-#pragma unroll
-                    for (int a = 0; a < B; a++) {
-                        const int jo = jb * B + a;
-                        const float num = (h[fi] - omw * red[a]) + (x[fi] * cw[fi] - w * g[fi]);
-                        const float xn = num * inv[fi];
-                        const float dl = __shfl_sync(0xffffffffu, xn - x[fi], jo, G);
-                        if (j == jo) x[fi] = xn;
-                        dls[a] = dl;
-#pragma unroll
-                        for (int b2 = a + 1; b2 < B; b2++) red[b2] = fmaf(dl, red[q++], red[b2]);
-                        const float *srow = Ss + (f0 + a) * D + j;
-#pragma unroll
-                        for (int i = 0; i < KPL; i++) g[i] = fmaf(dl, srow[i * G], g[i]);
-                    }
-                }
-#pragma unroll
-                for (int e = 0; e < E; e++)
-#pragma unroll
-                    for (int a = 0; a < B; a++) pred[e] = fmaf(dls[a], ye[e][a], pred[e]);
-            }
-        }
-        if (act) {
-#pragma unroll
-            for (int i = 0; i < KPL; i++) X[(int64_t)r * D + i * G + j] = x[i];
-        }
-        __syncwarp();   // the next row's staging must not overtake this row's column reads
-    }
-}
-
 // ---- lane-group form with BLOCKED staging (round 2) ------------------------------------------------------------------
-// Same arithmetic as als_rows_group_kernel (B = 1), but the gathered rows are staged one block of G coordinates at a time
-// instead of whole: n * (G+1) floats per row in shared memory instead of n * (D+1).  The whole-row version held 33 KB (rows up
+// The arithmetic above with the gathered rows staged one block of G coordinates at a time instead of whole (round 1's
+// als_rows_group_kernel, removed): n * (G+1) floats per row in shared memory instead of n * (D+1).  The whole-row version held 33 KB (rows up
 // to 32 entries, two rows per warp) / 49.5 KB (rows up to 96 entries) per warp next to the 64 KB copy of S, i.e. 3-4 warps per
 // SM, and each of those warps runs a dependent shuffle chain per coordinate: 2.3 + 3.0 ms per half-sweep for 7 % of the rows
 // (profiles/r02_launches_c3.md).  Lane j of the group owns coordinate i*G + j of block i, so a block is exactly what the group
@@ -740,8 +587,7 @@ static int32_t run_gram(gorse_b200_cf *cf, int side, const float *X_base, const 
 {
     gorse_b200_ctx *c = cf->ctx;
     const int d = cf->d, dd = d * d;
-    static const bool no_tc = [] { const char *e = getenv("GORSE_B200_ALS_NO_TC"); return e && atoi(e) == 1; }();   // A/B runs
-    if (d == 128 && !no_tc) {
+    if (d == 128) {
         // S = sum of x x^T over the rows with feedback: the same tensor-core kernel as the row Grams, fed with the list of
         // those rows in chunks of GB_ALS_CHUNK (als_gram_tc.cu); the chunk partials are summed in order (deterministic)
         const int nc = cf->als_s_chunks[side];
@@ -784,7 +630,7 @@ static int32_t run_gram(gorse_b200_cf *cf, int side, const float *X_base, const 
 
 // rows bucketed by length, one launch per class:
 //   d % 32 == 0, d <= 128:  n <= 4 | n <= 8 | n <= 16  one THREAD per row (als_thread.cu)
-//                           n <= 32 (16 lanes per row) | n <= 96 (a warp per row)  lane-group form (als_rows_group_kernel)
+//                           n <= 32 (16 lanes per row) | n <= 96 (a warp per row)  lane-group form (als_rows_group_blocked_kernel)
 //                           longer -> Gram form
 //   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp)
 //   longer -> Gram form when d <= 128, else gathered from L2 without staging
@@ -895,45 +741,8 @@ static int32_t prepare_als(gorse_b200_cf *cf)
     return GORSE_B200_OK;
 }
 
-template <int G, int E, int KPL, int B>
-static int32_t launch_group_b(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
-                            const int32_t *rows, int32_t n_rows)
-{
-    gorse_b200_ctx *c = cf->ctx;
-    constexpr int D = G * KPL, DP = D + 1;
-    const size_t s_bytes = sizeof(float) * D * D, per_warp = sizeof(float) * (32 / G) * group_stage_floats(G, E, DP);
-    const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024 - s_bytes) / per_warp));
-    const size_t sm = s_bytes + warps * per_warp;
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / (32 * warps), (227 * 1024) / (sm + 1024)));
-    const int groups_per_cta = warps * (32 / G);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_rows + groups_per_cta - 1) / groups_per_cta, (int64_t)c->sm_count * ctas_per_sm));
-    GB_CUDA(cudaFuncSetAttribute(als_rows_group_kernel<G, E, KPL, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    als_rows_group_kernel<G, E, KPL, B><<<grid, 32 * warps, sm, c->stream>>>(X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows);
-    GB_LAUNCHED(c);
-    return GORSE_B200_OK;
-}
-
-// (Resolving four coordinates per shuffle butterfly -- B = 4 -- was measured SLOWER at C3 in round 1, 72 vs 43 ms/epoch:
-// the lane-group kernels are bound by shuffle / shared-memory issue, not by the latency of the dependent chain.)
-template <int G, int E, int KPL>
-static int32_t launch_group(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
-                            const int32_t *rows, int32_t n_rows)
-{
-    return launch_group_b<G, E, KPL, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows);
-}
-
-template <int G, int E>
-static int32_t launch_group_d(gorse_b200_cf *cf, float *X, const float *Y, const int64_t *off, const int32_t *idx, float reg, float w,
-                              const int32_t *rows, int32_t n_rows)
-{
-    switch (cf->d / 32) {
-        case 1: return launch_group<G, E, 32 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
-        case 2: return launch_group<G, E, 64 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
-        case 3: return launch_group<G, E, 96 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
-        default: return launch_group<G, E, 128 / G>(cf, X, Y, off, idx, reg, w, rows, n_rows);
-    }
-}
-
+// (Round 1's whole-row lane-group kernel and its B = 4 variant -- four coordinates per shuffle butterfly, 72 vs 43 ms/epoch --
+// are gone: the blocked-staging kernel above replaced them in every class, profiles/r02_launches_c3.md.)
 static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, const int64_t *off, const int32_t *idx,
                         float reg, float w, float *pred_scratch)
 {
@@ -954,8 +763,7 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
                 case 4: ck = als_chunk_gram_kernel<4, false>; break;
                 default: ck = als_chunk_gram_kernel<8, false>; break;
             }
-            static const bool no_tc = [] { const char *e = getenv("GORSE_B200_ALS_NO_TC"); return e && atoi(e) == 1; }();   // A/B runs
-            if (d == 128 && !no_tc) {
+            if (d == 128) {
                 GB_TRY(als_chunk_gram_tc(c, Y, idx, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, nc, cf->als_partial.p));
             } else {
                 ck<<<nc, 256, gsm, c->stream>>>(Y, d, idx, cf->als_chunk_row[side].p, cf->als_chunk_begin[side].p, cf->als_chunk_len[side].p, cf->als_partial.p);
@@ -973,22 +781,15 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
         }
         if (grouped && k != GB_ALS_LONG) {
             const RowClass rc = kRowClasses[k];
-            // A/B (round 2): rows with more than GORSE_B200_ALS_THREAD_MAX entries leave the thread-per-row kernel for a lane
-            // group of 8 / 16 lanes with blocked staging
-            static const int thread_max = [] { const char *e = getenv("GORSE_B200_ALS_THREAD_MAX"); return e ? atoi(e) : 4; }();
-            if (rc.kind == 0 && rc.max_n <= thread_max) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
+            // Round 2 A/B (profiles/r02_launches_c3.md): lane groups with blocked staging beat the thread-per-row kernel in
+            // every class above 4 entries (<=8: 0.80 vs 1.16 ms, <=16: 1.27 vs 1.99 ms per half-sweep at C3) and the
+            // whole-row staging of the first lane-group kernels in the two longer classes; the thread kernel keeps the
+            // shortest rows, where it is 0.14 ms ahead.
+            if (rc.kind == 0 && rc.max_n <= 4) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
             else if (rc.kind == 0 && rc.max_n <= 8) GB_TRY((launch_group_blocked_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else if (rc.kind == 0) GB_TRY((launch_group_blocked_d<16, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-            else {
-                static const bool whole = [] { const char *e = getenv("GORSE_B200_ALS_WHOLE_ROWS"); return e && atoi(e) == 1; }();   // A/B
-                if (rc.G == 16) {
-                    if (whole) GB_TRY((launch_group_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-                    else GB_TRY((launch_group_blocked_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-                } else {
-                    if (whole) GB_TRY((launch_group_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-                    else GB_TRY((launch_group_blocked_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
-                }
-            }
+            else if (rc.G == 16) GB_TRY((launch_group_blocked_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else GB_TRY((launch_group_blocked_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             continue;
         }
         // one warp per row; the long class without a Gram form (d > 128) gathers from L2 without staging

@@ -53,7 +53,6 @@ struct Params {
     int32_t *cand_cnt;    // [nq][2] pushes per column half (may exceed HALF_CAP)
     float *theta;         // [nq][2] threshold used by each half
     float *dbg;           // optional dense [nq][n_tiles*128] score dump (tests)
-    int32_t exp;          // TEMPORARY timing experiments (GORSE_B200_TOPK_EXP): 1 no hits(), 2 no tcgen05.ld either, 4 theta = +inf
 };
 
 // instruction descriptor: D fp32 (bits 4-5 = 1), A/B bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 at 17, M>>4 at 24
@@ -92,15 +91,15 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     uint8_t *smem_b = smem_a + (size_t)TILES_M * P.kb * TILE_BYTES;      // [STAGES][kb] tiles
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_b + (size_t)STAGES * P.kb * TILE_BYTES);
     uint64_t *full = bars, *empty = bars + STAGES, *a_full = bars + 2 * STAGES, *a_empty = a_full + 1;
-    uint64_t *t_full = a_empty + 1, *t_empty = t_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+    uint64_t *t_full = a_empty + 1, *t_empty = t_full + 4;   // one pair per accumulator (tile m, stage as): index m * 2 + as
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
-        for (int s = 0; s < 2; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], EPI_WARPS); }
+        for (int s = 0; s < 4; s++) { mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], EPI_WARPS / TILES_M); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -163,13 +162,18 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 mbar_wait_backoff(a_full, ag & 1);
                 for (int t = 0; t < total_tiles; t++, it++, at++) {
                     const uint32_t s = it % STAGES, as = at & 1;
-                    mbar_wait(&t_empty[as], ((at >> 1) & 1) ^ 1);  // epilogue drained this accumulator stage
                     mbar_wait(&full[s], (it / STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    if (elect_one()) {
-                        const uint32_t b_lo = b_lo0 + s * stage16;
+                    const uint32_t b_lo = b_lo0 + s * stage16;
 #pragma unroll
-                        for (int m = 0; m < TILES_M; m++) {
+                    for (int m = 0; m < TILES_M; m++) {
+                        // hand-off per ACCUMULATOR, not per pair: an accumulator is refilled every 2 steps, and from the commit of
+                        // its MMAs to the first MMA of the refill (commit -> epilogue wakes -> tcgen05.ld -> arrive -> this warp
+                        // wakes -> issue -> tensor pipe) ~1300 cycles pass (tools/micro/umma_pipe.cu).  With one barrier per
+                        // stage that latency followed 1024 cycles of MMAs of both tiles (budget 2048: period 1175+); per
+                        // accumulator it follows 512.
+                        mbar_wait(&t_empty[m * 2 + as], ((at >> 1) & 1) ^ 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        if (elect_one()) {
                             const uint32_t d = tmem_base + (uint32_t)((m * 2 + as) * BN);
                             const uint32_t a_lo = a_lo0 + (uint32_t)m * stage16;
                             for (uint32_t kb = 0; kb < (uint32_t)P.kb; kb++) {
@@ -179,9 +183,10 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                     umma_bf16(d, desc(a_lo + off, a_hi), desc(b_lo + off, b_hi), IDESC, (kb | k) != 0);
                                 }
                             }
+                            if (m == TILES_M - 1) umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
+                            umma_commit(&t_full[m * 2 + as]);
                         }
-                        umma_commit(&empty[s]);      // B stage reusable once these MMAs retire
-                        umma_commit(&t_full[as]);    // both accumulators of this stage are complete
+                        __syncwarp();
                     }
                     __syncwarp();
                 }
@@ -200,7 +205,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         auto release = [&](int as) {      // the accumulators of stage `as` are in registers: hand the stage back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[as]);
+            if (lane == 0) mbar_arrive(&t_empty[m * 2 + as]);
         };
         for (int g = blockIdx.x; g < P.n_groups; g += gridDim.x) {
             const int64_t row = (int64_t)(g * TILES_M + m) * BM + (ew & 3) * 32 + lane;
@@ -229,7 +234,7 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 };
                 for (int t = 0; t < P.m_tiles; t++, at++) {
                     const int as = at & 1;
-                    mbar_wait(&t_full[as], (at >> 1) & 1);
+                    mbar_wait(&t_full[m * 2 + as], (at >> 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
                     for (int c0 = 0; c0 < BN / 2; c0 += 32) {
@@ -267,7 +272,6 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");   // lists are free for the pushes from here
                 theta = row_ok ? top[R_TOP - 1] - 2.f * P.eps[row] : INFINITY;   // padding rows never hit
-                if (P.exp & 4) theta = INFINITY;
             }
             // ---- the sweep: every column at or above theta goes to the row's list
             int cnt = 0;
@@ -302,17 +306,15 @@ topk_mma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             for (int t = P.m_tiles; t < total_tiles; t++, at++) {
                 const int as = at & 1;
                 const int bt = t < P.n_tiles ? t : t - P.n_tiles;
-                mbar_wait(&t_full[as], (at >> 1) & 1);
+                mbar_wait(&t_full[m * 2 + as], (at >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // both batches into registers, then the stage goes back BEFORE they are looked at: a warp that has hits to
                 // push delays only itself, not the 15 others and the tensor pipe (see the note above the kernel)
                 uint32_t v0[32], v1[32];
-                if (P.exp & 2) { release(as); continue; }
                 tmem_ld32_issue(acc0 + (uint32_t)(as * BN), v0);
                 tmem_ld32_issue(acc0 + (uint32_t)(as * BN + 32), v1);
                 tmem_ld_wait();
                 release(as);
-                if (P.exp & 1) { if (v0[0] == 0x12345678u && v1[5] == 0x1234567u) cnt++; continue; }
                 const int64_t col0 = (int64_t)bt * BN + half * (BN / 2);
                 if constexpr (DBG) {
                     if (t < P.n_tiles) { dump(v0, col0); dump(v1, col0 + 32); }
@@ -572,17 +574,19 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
     const int64_t n_pad = (ix->n + mma::BN - 1) / mma::BN * mma::BN;
     const int n_tiles = (int)(n_pad / mma::BN);
     // sample size: the R_TOP-th best of m random columns leaves on average R_TOP * N / m columns above it (Gamma(R_TOP)
-    // spread).  Aim for 3.2k per column half: fewer than k with probability ~2e-4, and the HALF_CAP-slot candidate list
-    // overflows with probability ~1e-5.  (Round 2 tried 4.5k and 6k to get rid of the ~30 fallback rows per 151 552-row call:
-    // the lists, already inflated 1.35x by the -2 eps on theta, then overflow for 1 % / 20 % of the rows and the exact
-    // fallback takes over: 398 ms / 4.6 s per call instead of 68 ms.  profiles/r02_topk_margin_chunk.md.)
-    static const double margin = [] { const char *e = getenv("GORSE_B200_TOPK_MARGIN"); return e ? atof(e) : 4.0; }();   // A/B
-    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (margin * k) / mma::BN);
+    // spread).  Both column halves of a row now share ONE threshold from the whole sample, aimed at 4k columns per row: the
+    // row has fewer than k candidates when >= R_TOP of its true top k fell into the sample, Poisson(k m / N = R_TOP / 4):
+    // ~1e-6 per row (0 rows of 151 552 measured; at 3.2k: 25 rows, each a full exact scan; at 2.4k: 690), and a half's
+    // HALF_CAP-slot list holds 4x the expected count.  (Round 1 / early round 2: 3.2k PER HALF, lists overflowing for ~35
+    // rows per call; 4.5k / 6k per half overflowed for 1 % / 20 % of the rows.  profiles/r02_topk_margin_chunk.md,
+    // profiles/r02_topk_epilogue.md.)
+    int m_tiles = (int)((double)mma::R_TOP * (double)ix->n / (4.0 * k) / mma::BN);
     m_tiles = std::max(1, std::min(m_tiles, n_tiles));
     const bool self_skip = d_q == nullptr;
     // stages from the shared-memory budget
     const size_t a_bytes = (size_t)mma::TILES_M * kb * mma::TILE_BYTES, b_stage = (size_t)kb * mma::TILE_BYTES;
-    int stages = (int)std::min<size_t>(4, (200 * 1024 - a_bytes) / b_stage);
+    // at most 4: a fifth stage fits (230 KB) but leaves the epilogue's global traffic no L1 and measured 6 % slower
+    int stages = (int)std::min<size_t>(4, (226 * 1024 - 1280 - a_bytes) / b_stage);
     if (stages < 2) { set_error("search_mma: Kp = %d does not fit", kp); return GORSE_B200_ERR_UNSUPPORTED; }
     const size_t smem = a_bytes + (size_t)stages * b_stage + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -630,7 +634,6 @@ int32_t search_mma(gorse_b200_index *ix, const float *d_q, const int64_t *d_qidx
         mma::Params P;
         P.n = ix->n; P.n_tiles = n_tiles; P.m_tiles = m_tiles; P.kb = kb; P.nq = n_this; P.n_groups = (int)(n_this_pad / 256);
         P.eps = eps.p; P.cand_col = ccol.p; P.cand_val = cval.p; P.cand_cnt = ccnt.p; P.theta = theta.p; P.dbg = ix->dbg_scores;
-        { const char *e = getenv("GORSE_B200_TOPK_EXP"); P.exp = e ? atoi(e) : 0; }
         const int grid = std::min(P.n_groups, c->sm_count);
         if (!ix->ev0) { cudaEventCreate(&ix->ev0); cudaEventCreate(&ix->ev1); }
         cudaEventRecord(ix->ev0, c->stream);

@@ -1,7 +1,10 @@
 #!/bin/bash
-# timing experiments on the sweep kernel (results are garbage with EXP != 0: only the first launch is timed, then the run is killed)
-for x in 0 4 1 2; do
-  echo "== GORSE_B200_TOPK_EXP=$x"
-  GORSE_B200_TOPK_EXP=$x timeout 300 ncu --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed,sm__cycles_elapsed.max -k regex:topk_mma_kernel -c 1 --kill yes --clock-control none python bench.py --workload c4 --steps 1 --warmup 0 --no-cpu --no-e2e --no-also > gpurun_out/exp_$x.csv 2>&1
-  grep "topk_mma_kernel" gpurun_out/exp_$x.csv | awk -F'","' '{print $(NF-2), $(NF-1), $NF}'
+for st in 4 5; do
+  echo "== GORSE_B200_TOPK_STAGES=$st"
+  GORSE_B200_TOPK_STAGES=$st timeout 300 python bench.py --workload c4 --no-cpu --no-e2e --steps 5 > gpurun_out/c4_st$st.json 2>gpurun_out/c4_st$st.err
+  python - <<PY
+import json
+d=json.loads(open('gpurun_out/c4_st$st.json').read().strip().splitlines()[-1])
+print("  ms/step %.1f  value %.3g  stage1 ms %.1f frac %.3f  fallback rows %d" % (d['ms_per_step'], d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['config']['fallback_rows']), d['clocks'])
+PY
 done
