@@ -44,6 +44,22 @@ def make_feedback(n_users, n_items, n_feedback, seed=0, zipf_s=1.0, n_clusters=0
     key.sort()  # (np.unique's hash path is ~6x slower at 10^7 keys)
     if key.size > 1:
         key = key[np.concatenate(([True], key[1:] != key[:-1]))]
+    # a dense matrix (ml-100k's shape: 6 % filled, Zipf head saturated) loses more than the 12 % over-draw to duplicates:
+    # keep drawing (same user activity, same item law) until enough distinct pairs exist
+    for _ in range(64 if exact else 0):
+        if key.size >= want or key.size >= n_users * n_items:
+            break
+        m = max(want - key.size, 1024) * 2
+        u2 = rng.choice(n_users, size=m, p=act / act.sum()).astype(np.int64)
+        r2 = np.minimum(np.searchsorted(cdf, rng.random(m)), n_items - 1)
+        if n_clusters > 0:
+            uc2 = u2 % n_clusters
+            rin2 = (r2 // n_clusters) * n_clusters + uc2
+            rin2 = np.where(rin2 >= n_items, uc2 % n_items, rin2)
+            i2 = np.where(rng.random(m) < in_cluster, rin2, r2)
+        else:
+            i2 = perm[r2]
+        key = np.unique(np.concatenate((key, u2 * np.int64(n_items) + i2.astype(np.int64))))
     if exact and key.size > want:
         # trim the surplus at random, never a user's first item (every user keeps >= 1)
         u_of = key // n_items

@@ -1,10 +1,6 @@
 #!/bin/bash
-for st in 4 5; do
-  echo "== GORSE_B200_TOPK_STAGES=$st"
-  GORSE_B200_TOPK_STAGES=$st timeout 300 python bench.py --workload c4 --no-cpu --no-e2e --steps 5 > gpurun_out/c4_st$st.json 2>gpurun_out/c4_st$st.err
-  python - <<PY
-import json
-d=json.loads(open('gpurun_out/c4_st$st.json').read().strip().splitlines()[-1])
-print("  ms/step %.1f  value %.3g  stage1 ms %.1f frac %.3f  fallback rows %d" % (d['ms_per_step'], d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['config']['fallback_rows']), d['clocks'])
-PY
-done
+# the driver's round-end scaling launch at N = 2 (both arms), plus the two tests that failed in the last full run
+timeout 300 python -m pytest tests/test_ncf.py -q 2>&1 | tail -3
+run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $1 bench.py --gpus 2 "${@:2}"; }
+timeout 400 bash -c "$(declare -f run); run 29621 --impl reference --steps 3 --warmup 1" > gpurun_out/scale_ref_n2.json 2> gpurun_out/scale_ref_n2.err; tail -2 gpurun_out/scale_ref_n2.err; python tools/show_bench.py gpurun_out/scale_ref_n2.json
+timeout 400 bash -c "$(declare -f run); run 29622 --steps 20 --warmup 5" > gpurun_out/scale_n2.json 2> gpurun_out/scale_n2.err; tail -2 gpurun_out/scale_n2.err; python tools/show_bench.py gpurun_out/scale_n2.json

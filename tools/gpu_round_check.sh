@@ -12,3 +12,7 @@ echo "== bench (default: c2 + also c3, c4)"
 timeout 400 python bench.py > $O/bench_default.json 2> $O/bench_default.err; tail -c 300 $O/bench_default.err; python tools/show_bench.py $O/bench_default.json
 echo "== reference arm"
 timeout 200 python bench.py --impl reference --steps 5 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; python tools/show_bench.py $O/bench_ref.json
+if [ -n "$WITH_LISTS" ]; then
+echo "== ncu launch lists (c2 c3 c4)"
+bash tools/ncu_lists.sh c2 c3 c4 > $O/lists.log 2>&1; tail -3 $O/lists.log
+fi
