@@ -293,7 +293,7 @@ __device__ __forceinline__ float group_sum(float v)
 //   sweep   per block: stage all n entries of the block, then the G coordinates as before.
 // Every entry is staged once per pass, as before (in G*4-byte pieces instead of whole rows).
 template <int G, int E, int KPL>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(G == 16 ? 1024 : 512)   // G = 16: 64 registers, 32 warps next to ONE copy of S
 als_rows_group_blocked_kernel(float *X, const float *Y, const int64_t *off, const int32_t *idx, const float *S, float reg, float w,
                               const int32_t *row_ids, int32_t n_rows)
 {
@@ -438,7 +438,7 @@ static int32_t launch_group_blocked(gorse_b200_cf *cf, float *X, const float *Y,
     gorse_b200_ctx *c = cf->ctx;
     constexpr int D = G * KPL, YS = E * G * (G + 1) + (G < 32 ? G : 0);
     const size_t s_bytes = sizeof(float) * D * D, per_warp = sizeof(float) * (32 / G) * YS;
-    const int warps = (int)std::max<size_t>(1, std::min<size_t>(16, (220 * 1024 - s_bytes) / per_warp));
+    const int warps = (int)std::max<size_t>(1, std::min<size_t>(G == 16 ? 32 : 16, (220 * 1024 - s_bytes) / per_warp));
     const size_t sm = s_bytes + warps * per_warp;
     const int groups_per_cta = warps * (32 / G);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)n_rows + groups_per_cta - 1) / groups_per_cta, (int64_t)c->sm_count));
@@ -536,17 +536,23 @@ __global__ void __launch_bounds__(256) als_partial_reduce_kernel(const int32_t *
     p[(int64_t)c0 * stride4 + e] = acc;
 }
 
-// one CTA per long row: its (already summed) partial -> A, one Gauss-Seidel sweep by warp 0
+// one CTA per long row: its (already summed) partial -> A, then one Gauss-Seidel sweep by warp 0 in RESIDUAL form:
+//     r = h - A x (all warps);   for f:  delta = r_f / A_ff,  x_f += delta,  r -= delta * A[:, f]
+// which is the same sweep (x_f + r_f / A_ff == (h_f - sum_{k != f} A_fk x_k) / A_ff) without a reduction on the sequential
+// chain: lane l holds r, x and 1 / A_kk for k = l + 32 j, a step is one multiply, one shuffle and d / 32 FMAs whose A operands
+// (column f, conflict-free thanks to the d + 1 row pitch) do not depend on the chain.  Round 1/2's version summed a
+// 128-element dot across the warp per coordinate (5 dependent shuffles + a divide): 1.03 ms per half-sweep at C3.
+// d % 32 == 0, d <= 128 (the only shapes prepare_als sends here).
 __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const float *S, float reg, float w, const int32_t *rows,
                                                         const int32_t *row_chunk0, const float *partial, int reduced)
 {
     extern __shared__ float sm[];
     float *A = sm;                 // [d][d+1]
-    float *h = A + d * (d + 1);    // [d]
+    float *h = A + d * (d + 1);    // [d]   h, then the residual
     float *x = h + d;              // [d]
     const int r = rows[blockIdx.x];
     const int c0 = row_chunk0[blockIdx.x], c1 = reduced ? c0 + 1 : row_chunk0[blockIdx.x + 1];
-    const int dd = d * d, stride = dd + d;
+    const int dd = d * d, stride = dd + d, dp = d + 1;
     const float omw = 1.0f - w;
     for (int e = threadIdx.x; e < dd; e += blockDim.x) {
         float g = 0.f;
@@ -554,7 +560,7 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
         const int i = e / d, j = e - i * d;
         float a = omw * g + w * __ldg(S + e);
         if (i == j) a += reg;
-        A[i * (d + 1) + j] = a;
+        A[i * dp + j] = a;
     }
     for (int e = threadIdx.x; e < d; e += blockDim.x) {
         float g = 0.f;
@@ -563,19 +569,52 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
         x[e] = X[(int64_t)r * d + e];
     }
     __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        for (int f = 0; f < d; f++) {
-            float s = 0.f;
-            for (int k = lane; k < d; k += 32)
-                if (k != f) s += x[k] * A[f * (d + 1) + k];   // A is symmetric: row f instead of column f
-            s = warp_sum(s);
-            const float xn = (h[f] - s) / A[f * (d + 1) + f];
-            __syncwarp();
-            if (lane == 0) x[f] = xn;
-            __syncwarp();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // residual rows k = wid, wid + nw, ...: r_k = h_k - A[k, :] x
+    float res[16];   // d / nw <= 16 rows per warp
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int k = wid + q * nw;
+        float s = 0.f;
+        if (k < d)
+            for (int jx = lane; jx < d; jx += 32) s += A[k * dp + jx] * x[jx];
+        res[q] = warp_sum(s);
+    }
+    __syncthreads();   // every warp has read h's neighbours' x; now h becomes the residual
+#pragma unroll
+    for (int q = 0; q < 16; q++) {
+        const int k = wid + q * nw;
+        if (k < d && lane == 0) h[k] -= res[q];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int kpl = d >> 5;
+        float rr[4], xv[4], inv[4];
+#pragma unroll
+        for (int jx = 0; jx < 4; jx++) {
+            const int k = lane + 32 * jx;
+            const bool ok = jx < kpl;
+            rr[jx] = ok ? h[k] : 0.f;
+            xv[jx] = ok ? x[k] : 0.f;
+            inv[jx] = ok ? 1.0f / A[k * dp + k] : 0.f;
         }
-        for (int k = lane; k < d; k += 32) X[(int64_t)r * d + k] = x[k];
+#pragma unroll
+        for (int jf = 0; jf < 4; jf++) {
+            if (jf < kpl) {
+#pragma unroll 4
+                for (int o = 0; o < 32; o++) {
+                    const int f = 32 * jf + o;
+                    const float delta = __shfl_sync(0xffffffffu, rr[jf] * inv[jf], o);
+                    if (lane == o) xv[jf] += delta;
+#pragma unroll
+                    for (int jx = 0; jx < 4; jx++)
+                        if (jx < kpl) rr[jx] = fmaf(-delta, A[(lane + 32 * jx) * dp + f], rr[jx]);
+                }
+            }
+        }
+#pragma unroll
+        for (int jx = 0; jx < 4; jx++)
+            if (jx < kpl) X[(int64_t)r * d + lane + 32 * jx] = xv[jx];
     }
 }
 

@@ -198,12 +198,14 @@ template <int D>
 static int32_t launch_thread_d(gorse_b200_ctx *c, int nmax, float *X, const float *Y, const int64_t *off, const int32_t *idx,
                                const float *S, float reg, float w, const int32_t *rows, int32_t n_rows)
 {
+    // Only the shortest class runs here since the end of round 2: NMAX = 8 / 16 (staging blocks of 16 / 8 coordinates) lost
+    // to the lane-group kernels with blocked staging, 1.16 vs 0.80 and 1.99 vs 1.27 ms per half-sweep at C3.
     if (nmax <= 4) return launch_thread_rows<D, 4, 32>(c, X, Y, off, idx, S, reg, w, rows, n_rows);
-    if (nmax <= 8) return launch_thread_rows<D, 8, 16>(c, X, Y, off, idx, S, reg, w, rows, n_rows);
-    return launch_thread_rows<D, 16, 8>(c, X, Y, off, idx, S, reg, w, rows, n_rows);
+    set_error("als_thread_rows: rows of up to %d entries do not run on the thread-per-row kernel", nmax);
+    return GORSE_B200_ERR_UNSUPPORTED;
 }
 
-// rows with at most `nmax` (<= 16) entries, d in {32, 64, 96, 128}
+// rows with at most `nmax` (<= 4) entries, d in {32, 64, 96, 128}
 int32_t als_thread_rows(gorse_b200_ctx *c, int d, int nmax, float *X, const float *Y, const int64_t *off, const int32_t *idx,
                         const float *S, float reg, float w, const int32_t *rows, int32_t n_rows)
 {
