@@ -554,19 +554,42 @@ __global__ void __launch_bounds__(256) als_solve_kernel(float *X, int d, const f
     const int c0 = row_chunk0[blockIdx.x], c1 = reduced ? c0 + 1 : row_chunk0[blockIdx.x + 1];
     const int dd = d * d, stride = dd + d, dp = d + 1;
     const float omw = 1.0f - w;
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-        float g = 0.f;
-        for (int c = c0; c < c1; c++) g += partial[(int64_t)c * stride + e];
-        const int i = e / d, j = e - i * d;
-        float a = omw * g + w * __ldg(S + e);
-        if (i == j) a += reg;
-        A[i * dp + j] = a;
-    }
-    for (int e = threadIdx.x; e < d; e += blockDim.x) {
-        float g = 0.f;
-        for (int c = c0; c < c1; c++) g += partial[(int64_t)c * stride + dd + e];
-        h[e] = g;
-        x[e] = X[(int64_t)r * d + e];
+    if (reduced) {
+        // the row's partial is one (G, h) block, 16-byte aligned (d % 4 == 0): float4 loads, four in flight per thread.  (The
+        // scalar loop below it has a run-time inner trip count, so its 64 loads per thread went out one DRAM latency after
+        // the other: 0.27 + 1.13 ms per epoch at C3 for what is 0.13 GB of traffic.)
+        const float4 *p4 = reinterpret_cast<const float4 *>(partial + (int64_t)c0 * stride);
+        const float4 *s4 = reinterpret_cast<const float4 *>(S);
+#pragma unroll 4
+        for (int e4 = threadIdx.x; e4 < dd / 4; e4 += blockDim.x) {
+            const float4 g = p4[e4], sv = __ldg(s4 + e4);
+            const int e = 4 * e4, i = e / d, j = e - i * d;     // the four elements share row i
+            float a[4] = {omw * g.x + w * sv.x, omw * g.y + w * sv.y, omw * g.z + w * sv.z, omw * g.w + w * sv.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (i == j + q) a[q] += reg;
+                A[i * dp + j + q] = a[q];
+            }
+        }
+        for (int e = threadIdx.x; e < d; e += blockDim.x) {
+            h[e] = partial[(int64_t)c0 * stride + dd + e];
+            x[e] = X[(int64_t)r * d + e];
+        }
+    } else {
+        for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+            float g = 0.f;
+            for (int c = c0; c < c1; c++) g += partial[(int64_t)c * stride + e];
+            const int i = e / d, j = e - i * d;
+            float a = omw * g + w * __ldg(S + e);
+            if (i == j) a += reg;
+            A[i * dp + j] = a;
+        }
+        for (int e = threadIdx.x; e < d; e += blockDim.x) {
+            float g = 0.f;
+            for (int c = c0; c < c1; c++) g += partial[(int64_t)c * stride + dd + e];
+            h[e] = g;
+            x[e] = X[(int64_t)r * d + e];
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -674,11 +697,13 @@ static int32_t run_gram(gorse_b200_cf *cf, int side, const float *X_base, const 
 //   otherwise (als_rows_kernel, one warp per row):  n*(d+1) <= 3072 floats (12 KB/warp) | <= 12288 (48 KB/warp)
 //   longer -> Gram form when d <= 128, else gathered from L2 without staging
 static const int kStageFloats[2] = {3072, 12288};
-#define GB_ALS_CLASSES 6
-#define GB_ALS_LONG 5   // index of the long-row class
+#define GB_ALS_CLASSES 7
+#define GB_ALS_LONG 6   // index of the long-row class
 // kind 0: thread per row (max_n entries); kind 1: lane group of G lanes, E entries per lane
 struct RowClass { int max_n, kind, G, E; };
-static const RowClass kRowClasses[GB_ALS_LONG] = {{4, 0, 0, 0}, {8, 0, 0, 0}, {16, 0, 0, 0}, {32, 1, 16, 2}, {96, 1, 32, 3}};
+// (33..64 entries are a class of their own since the end of round 2: 8.4 instead of 12.7 KB of staging per warp -> 16 warps
+// per SM instead of 12)
+static const RowClass kRowClasses[GB_ALS_LONG] = {{4, 0, 0, 0}, {8, 0, 0, 0}, {16, 0, 0, 0}, {32, 1, 16, 2}, {64, 1, 32, 2}, {96, 1, 32, 3}};
 
 static bool als_grouped(const gorse_b200_cf *cf) { return cf->d % 32 == 0 && cf->d <= 128; }
 
@@ -828,6 +853,7 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             else if (rc.kind == 0 && rc.max_n <= 8) GB_TRY((launch_group_blocked_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else if (rc.kind == 0) GB_TRY((launch_group_blocked_d<16, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else if (rc.G == 16) GB_TRY((launch_group_blocked_d<16, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
+            else if (rc.E == 2) GB_TRY((launch_group_blocked_d<32, 2>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else GB_TRY((launch_group_blocked_d<32, 3>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             continue;
         }

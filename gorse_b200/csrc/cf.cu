@@ -298,11 +298,11 @@ int32_t gorse_b200_cf_destroy(gorse_b200_cf *cf)
     cf->hot_items.free(); cf->hot_slot.free(); cf->hot.free(); cf->hotq.free(); cf->hot_sorted.free(); cf->hot_ctr.free();
     cf->gram.free(); cf->scratch.free();
     for (int a = 0; a < 2; a++) {
-        for (int b = 0; b < 6; b++) cf->als_rows[a][b].free();
+        for (int b = 0; b < 7; b++) cf->als_rows[a][b].free();
         cf->als_chunk_row[a].free(); cf->als_chunk_len[a].free(); cf->als_row_chunk0[a].free(); cf->als_chunk_begin[a].free();
         cf->als_s_rows[a].free(); cf->als_s_len[a].free(); cf->als_s_begin[a].free();
     }
-    cf->als_partial.free();
+    cf->als_partial.free(); cf->als_pred.free();
     delete cf;
     return GORSE_B200_OK;
 }

@@ -59,8 +59,8 @@ struct gorse_b200_cf {
     gb::DevBuf<float> gram;      // d x d
     gb::DevBuf<float> als_pred;  // eALS scratch: one prediction per entry of the longer CSR side, kept across epochs
     gb::DevBuf<float> scratch;   // per-row pred/res for long rows + partial grams
-    gb::DevBuf<int32_t> als_rows[2][6];  // [side][class] row ids bucketed by length (built lazily; als.cu prepare_als)
-    int32_t als_rows_n[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    gb::DevBuf<int32_t> als_rows[2][7];  // [side][class] row ids bucketed by length (built lazily; als.cu prepare_als)
+    int32_t als_rows_n[2][7] = {{0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0}};
     bool als_ready = false;
     // long rows in Gram form: chunk work list per side and the partial (G, h) scratch
     int32_t als_n_chunks[2] = {0, 0};
