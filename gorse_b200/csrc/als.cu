@@ -848,7 +848,8 @@ static int32_t run_rows(gorse_b200_cf *cf, int side, float *X, const float *Y, c
             // Round 2 A/B (profiles/r02_launches_c3.md): lane groups with blocked staging beat the thread-per-row kernel in
             // every class above 4 entries (<=8: 0.80 vs 1.16 ms, <=16: 1.27 vs 1.99 ms per half-sweep at C3) and the
             // whole-row staging of the first lane-group kernels in the two longer classes; the thread kernel keeps the
-            // shortest rows, where it is 0.14 ms ahead.
+            // shortest rows, where it is 0.14 ms ahead (also when they are many: the 300 K short user rows of C3 take 1.69 ms
+            // there and 2.0 ms on the 8-lane kernel).
             if (rc.kind == 0 && rc.max_n <= 4) GB_TRY(als_thread_rows(c, cf->d, rc.max_n, X, Y, off, idx, cf->gram.p, reg, w, rows, n_rows));
             else if (rc.kind == 0 && rc.max_n <= 8) GB_TRY((launch_group_blocked_d<8, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));
             else if (rc.kind == 0) GB_TRY((launch_group_blocked_d<16, 1>(cf, X, Y, off, idx, reg, w, rows, n_rows)));

@@ -1,4 +1,5 @@
 #!/bin/bash
-# ncu --set full of the lane-group row kernels of one C3 half-sweep (user side)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'als_rows_group_blocked_kernel' -c 5 -o gpurun_out/als_group_r2 -f python bench.py --workload c3 --steps 1 --warmup 1 --no-cpu --no-e2e --no-also > /dev/null 2>&1
-ls -la gpurun_out/als_group_r2.ncu-rep
+# eALS re-check after a kernel change: parity tests, launch list, C3 bench line
+timeout 400 python -m pytest tests/test_als_gpu.py tests/test_xl_als_gpu.py tests/test_fit_gpu.py -q 2>&1 | tail -3
+bash tools/ncu_lists.sh c3 2>&1 | grep "als_\|gram" | head -12
+python bench.py --workload c3 --no-cpu --no-e2e > gpurun_out/c3_new.json; python tools/show_bench.py gpurun_out/c3_new.json
