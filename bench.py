@@ -93,8 +93,14 @@ class ClockSampler:
         if not self.proc:
             return None
         time.sleep(0.12)
+        for _ in range(20):                      # nvidia-smi needs 0.1-0.3 s for its first line: never return without one
+            if self.rows:
+                break
+            time.sleep(0.05)
         self.proc.terminate()
-        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.12 and len(r) >= 7] or [r for (_, r) in self.rows if len(r) >= 7]
+        # samples inside the timed region; a region shorter than the 50 ms period takes the samples next to it
+        rows = ([r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.12 and len(r) >= 7]
+                or [r for (t, r) in sorted(self.rows, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:2] if len(r) >= 7])
         if not rows:
             return None
         sm = sorted(float(r[0]) for r in rows)
@@ -236,12 +242,12 @@ def run_bpr(args):
     ctx.sync()
 
     # ---- device-resident timing: K epochs, CUDA events on the library's own stream, max over ranks ----
+    sampler = ClockSampler(local) if rank == 0 else None   # started before the warm-up so that it is already printing
     for w in range(args.warmup):
         model.bpr_epoch(LR, REG, steps_per_epoch, 100 + w)
     ctx.barrier()
     if dist:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ctx.launch_count()
     t0 = time.time()
     ctx.timer_begin()
@@ -288,14 +294,21 @@ def run_bpr(args):
             hq = gb.PinnedArray((n_items, d))
             p_base = C.c_void_p(hp.array.ctypes.data - rank * upr * d * 4)   # the ABI takes the base of the FULL user table
             e_epochs = max(1, args.e2e_epochs)
-            if dist:
-                dist.barrier()
-            w0 = time.time()
-            m2 = gb.CFModel(ctx, n_users, n_items, d, off, items)
-            res = m2.fit("bpr", test_off, test_items, None, None, n_epochs=e_epochs, verbose=10, seed=0)
-            gb.check(gb.lib.gorse_b200_cf_get_factors(m2.h, p_base, gb.ptr(hq.array)))
-            w1 = time.time()
-            e_sec = max_over_ranks(w1 - w0)
+            # three complete, independent calls; the MEDIAN wall time is reported (one call is ~0.4 s of device work plus
+            # host work -- CSR validation/sort on 16 threads, plan set-up -- that moved 0.62 -> 1.31 s between boxes and runs)
+            walls = []
+            for _rep in range(3):
+                if dist:
+                    dist.barrier()
+                w0 = time.time()
+                m2 = gb.CFModel(ctx, n_users, n_items, d, off, items)
+                r_ = m2.fit("bpr", test_off, test_items, None, None, n_epochs=e_epochs, verbose=10, seed=0)
+                gb.check(gb.lib.gorse_b200_cf_get_factors(m2.h, p_base, gb.ptr(hq.array)))
+                w1 = time.time()
+                m2.close()
+                m2 = None
+                walls.append((max_over_ranks(w1 - w0), float(r_.ndcg), int(r_.epochs_run)))
+            e_sec, e_ndcg, e_run = sorted(walls)[1]
             finite = bool(np.isfinite(hq.array).all() and np.isfinite(hp.array).all())
             if max_over_ranks(0.0 if finite else 1.0) > 0.5:
                 raise FloatingPointError("non-finite factors after the end-to-end leg")
@@ -307,7 +320,7 @@ def run_bpr(args):
                    "what": f"per rank: cf_create (own CSR rows, host -> device) + gorse_b200_bpr_fit (Init, {e_epochs} epochs = reference default NEpochs, "
                            f"Evaluate at epoch 0 and every 10 epochs over all test users x 101 candidates with negatives sampled on the device, {n_eval} evaluations) "
                            f"+ get_factors into the pinned mirror; bytes are per rank and per epoch, amortised over the call",
-                   "wall_s": e_sec, "ndcg_at_10": float(res.ndcg), "epochs_run": int(res.epochs_run)}
+                   "wall_s": e_sec, "wall_s_all": [w for w, _, _ in walls], "ndcg_at_10": e_ndcg, "epochs_run": e_run}
         except Exception as ex:  # keep the contract line even if the end-to-end leg fails
             e2e_error = f"{type(ex).__name__}: {ex}"
         finally:
@@ -359,9 +372,9 @@ def run_als(args):
     with gb.Context(0) as ctx:
         with gb.CFModel(ctx, U, I, d, off, items, ioff, iusers) as m:
             m.init_normal(0.0, ALS_STD, 0)
+            sampler = ClockSampler(0)
             for _ in range(warm):
                 m.als_epoch(ALS_REG, ALS_ALPHA)
-            sampler = ClockSampler(0)
             l0, t0 = ctx.launch_count(), time.time()
             ctx.timer_begin()
             for _ in range(steps):

@@ -32,13 +32,18 @@ struct HotQueue {
 };
 
 // Opportunistically warp-aggregated append.  Returns false when the region is full (caller applies the triple itself).
+// The aggregation runs over whatever lanes happen to be converged (`__activemask()`, the coalesced-group pattern): each such
+// group elects a leader for ONE atomicAdd.  The four lanes of a quad always call this together (a quad owns one triple), but
+// independent thread scheduling does not promise that they sit in the same converged group, so the quad's verdict is
+// broadcast afterwards with the QUAD's own mask -- `__shfl_sync` then waits for exactly those four lanes (the
+// first version read lane4 == 0 through the opportunistic mask).
 __device__ __forceinline__ bool hotq_append(const HotQueue &hq, bool want, int lane4, int32_t slot, int32_t u, int32_t j)
 {
+    const int lane = threadIdx.x & 31;
     const unsigned act = __activemask();
     const unsigned m = __ballot_sync(act, want && lane4 == 0);
     bool ok = true;
     if (m) {
-        const int lane = threadIdx.x & 31;
         const int leader = __ffs(m) - 1;
         const int region = (int)((((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) % GB_HOTQ_REGIONS);
         unsigned long long base = 0;
@@ -51,10 +56,9 @@ __device__ __forceinline__ bool hotq_append(const HotQueue &hq, bool want, int l
                 e[0] = slot; e[1] = u; e[2] = j;
             } else ok = false;
         }
-        // every lane of a quad must agree
-        ok = __shfl_sync(act, ok, (lane & ~3)) != 0;
     }
-    return ok;
+    // every lane of a quad must agree with its lane 0
+    return __shfl_sync(0xFu << (lane & ~3), ok, lane & ~3) != 0;
 }
 
 // ---- counting sort of the queue by slot ---------------------------------------------------------
